@@ -1,0 +1,832 @@
+// capi.cu -- the extern "C" boundary of libsea_b200.so (see include/sea_b200.h for what each entry point replaces).
+// Host-side work that stays scalar: file headers, launch planning, VBR bucket counts (f32), table generation.
+// There is deliberately no CPU implementation of the codec here: a missing or failing GPU is an error return.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sea_b200.h"
+#include "sea_format.h"
+#include "sea_kernels.h"
+
+using namespace sea;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct sea_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int32_t *d_tab[9] = {};
+    DevTables tabs = {};
+    DevBuf in, out, streams, lens, chunk0, scratch, misc;
+    int *d_err = nullptr;
+    unsigned long long *d_ties = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    double last_kernel_ms = 0.0;
+    unsigned long long last_ties = 0;
+};
+
+struct sea_b200_encoder {
+    sea_b200_ctx *ctx;
+    sea_b200_settings settings;
+    EncodePlan plan;
+    uint32_t channels, sample_rate;
+    uint32_t chunk_size = 0;
+    int32_t *d_state = nullptr;
+};
+
+struct sea_b200_decoder {
+    sea_b200_ctx *ctx;
+    sea_b200_header header;
+    int sf_bits = -1;  // Decoder::init on the first chunk (file.rs:193-198)
+};
+
+namespace {
+
+int fail(sea_b200_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+int cuda_fail(sea_b200_ctx *ctx, cudaError_t e, const char *what)
+{
+    return fail(ctx, e == cudaErrorMemoryAllocation ? SEA_B200_ERR_NOMEM : SEA_B200_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);      \
+    } while (0)
+
+int map_dev_error(sea_b200_ctx *ctx, int dev_err)
+{
+    switch (dev_err) {
+        case kDevOk: return SEA_B200_OK;
+        case kDevInvalidFrame: return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "chunk type is neither CBR nor VBR (chunk.rs:81-85)");
+        default: return fail(ctx, SEA_B200_ERR_DOMAIN, "chunk data outside the reference's domain (it would panic: truncated or malformed chunk)");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decode core
+
+struct DecodeJob {
+    std::vector<DecStream> streams;
+    std::vector<uint64_t> n_samples;
+    uint64_t total_chains = 0;
+    bool uniform = true;
+    bool trailing_invalid_frame = false;  // streaming header with a short last chunk (chunk.rs:76-79)
+    sea_b200_header first = {};
+};
+
+// Resolve how many chunks/frames each stream yields: the host half of SeaDecoder::decode_frame (decoder.rs:33-59)
+// and SeaFile::samples_from_reader (file.rs:180-209).
+int plan_decode(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *headers, size_t header_stride, const uint64_t *sea_offsets,
+                const uint64_t *sea_lens, const uint64_t *pcm_offsets, const uint64_t *pcm_caps, DecodeJob *job)
+{
+    job->streams.resize(n_streams);
+    job->n_samples.assign(n_streams, 0);
+    uint64_t chain = 0;
+    for (uint32_t i = 0; i < n_streams; i++) {
+        sea_b200_header h;
+        const uint64_t len = sea_lens[i];
+        int rc = parse_file_header(headers + (size_t)i * header_stride, len < 22 ? len : 22, &h);
+        if (rc) return fail(ctx, rc, "stream " + std::to_string(i) + ": bad .sea header (file.rs:40-72)");
+        if (i == 0) job->first = h;
+        if (h.channels != job->first.channels || h.chunk_size != job->first.chunk_size || h.frames_per_chunk != job->first.frames_per_chunk)
+            job->uniform = false;
+        DecStream &d = job->streams[i];
+        memset(&d, 0, sizeof(d));
+        d.data_off = sea_offsets[i] + kFileHeaderBytes;  // metadata bytes are never skipped by the reference (file.rs:53-54)
+        d.data_len = len - kFileHeaderBytes;
+        d.pcm_off = pcm_offsets[i];
+        d.chunk_size = h.chunk_size;
+        d.frames_per_chunk = h.frames_per_chunk;
+        d.channels = h.channels;
+        const uint64_t avail_chunks = (d.data_len + h.chunk_size - 1) / h.chunk_size;
+        uint64_t frames;
+        if (h.total_frames > 0) {
+            const uint64_t want = ((uint64_t)h.total_frames + h.frames_per_chunk - 1) / h.frames_per_chunk;
+            const uint64_t n = std::min(want, avail_chunks);  // read of 0 bytes ends the stream quietly (file.rs:186-188)
+            d.n_chunks = (uint32_t)n;
+            frames = std::min<uint64_t>(h.total_frames, n * h.frames_per_chunk);
+        } else {
+            uint64_t n = d.data_len / h.chunk_size;
+            if (d.data_len % h.chunk_size) job->trailing_invalid_frame = true;
+            d.n_chunks = (uint32_t)n;
+            frames = n * h.frames_per_chunk;
+            if (frames > 0xffffffffull) return fail(ctx, SEA_B200_ERR_TOO_MANY_FRAMES, "stream longer than 2^32 frames");
+        }
+        d.total_frames = (uint32_t)frames;
+        const uint64_t samples = frames * h.channels;
+        if (pcm_caps && samples > pcm_caps[i]) return fail(ctx, SEA_B200_ERR_CAPACITY, "stream " + std::to_string(i) + ": PCM buffer too small");
+        job->n_samples[i] = samples;
+        if (chain + (uint64_t)d.n_chunks * h.channels > 0xfffffff0ull) return fail(ctx, SEA_B200_ERR_INVALID_PARAMETERS, "batch too large (2^32 chains)");
+        d.chain_begin = (uint32_t)chain;
+        chain += (uint64_t)d.n_chunks * h.channels;
+    }
+    job->total_chains = chain;
+    return SEA_B200_OK;
+}
+
+// d_sea / d_pcm are device pointers; first_hdr_word = first 4 bytes of the first chunk of stream 0 (host copy).
+int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t sea_len, int16_t *d_pcm, bool have_hdr_word,
+               uint32_t hdr_word)
+{
+    const uint32_t n_streams = (uint32_t)job.streams.size();
+    if (job.total_chains == 0) return SEA_B200_OK;
+    CU(ctx->streams.reserve(sizeof(DecStream) * n_streams));
+    CU(cudaMemcpyAsync(ctx->streams.p, job.streams.data(), sizeof(DecStream) * n_streams, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+
+    DecFastParams fp = {};
+    bool fast = false;
+    if (job.uniform && have_hdr_word && (reinterpret_cast<uint64_t>(d_sea) & 15u) == 0) {
+        fp.channels = job.first.channels;
+        fp.N = job.first.frames_per_chunk;
+        fp.chunk_size = job.first.chunk_size;
+        fp.hdr_word = hdr_word;
+        fp.s = (hdr_word >> 12) & 15u;
+        fp.b = (hdr_word >> 8) & 15u;
+        fp.F = (hdr_word >> 16) & 255u;
+        fp.n_streams = n_streams;
+        fp.total_chunks = job.total_chains / fp.channels;
+        const uint32_t type = hdr_word & 255u;
+        fast = (type == 1u || type == 2u) && (hdr_word >> 24) == 0x5Au && decode_fast_supported(fp);
+    }
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    int dev_err = 0;
+    if (fast) {
+        CU(launch_decode_fast(d_sea, sea_len, d_pcm, ctx->streams.as<DecStream>(), fp, ctx->tabs, ctx->d_err, ctx->stream));
+        ctx->launches++;
+        CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (dev_err != kDevOk) {  // some chunk is not what the fast path was specialised for: redo everything generically
+            fast = false;
+            CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+        }
+    }
+    if (!fast) {
+        CU(launch_decode_generic(d_sea, d_pcm, ctx->streams.as<DecStream>(), n_streams, job.total_chains, ctx->tabs, ctx->d_err, ctx->stream));
+        ctx->launches++;
+        CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return map_dev_error(ctx, dev_err);
+}
+
+// ------------------------------------------------------------------------------------------------ encode core
+
+struct EncodeJob {
+    EncodePlan plan;
+    EncParams params;
+    std::vector<EncStream> streams;
+};
+
+int plan_encode(sea_b200_ctx *ctx, uint32_t n_streams, const uint64_t *pcm_offsets, const uint32_t *n_frames, uint32_t sample_rate,
+                uint32_t channels, const sea_b200_settings *st, const uint64_t *out_offsets, bool raw_chunk_mode, EncodeJob *job)
+{
+    int rc = make_encode_plan(channels, st, &job->plan);
+    if (rc) return fail(ctx, rc, "encoder settings rejected (outside the reference's domain)");
+    const EncodePlan &pl = job->plan;
+    EncParams &p = job->params;
+    memset(&p, 0, sizeof(p));
+    p.channels = channels;
+    p.N = pl.N;
+    p.F = pl.F;
+    p.s = pl.s;
+    p.hdr_bits = pl.hdr_bits;
+    p.vbr = pl.vbr;
+    p.base = pl.base;
+    p.full_counts[0] = pl.full_counts[0];
+    p.full_counts[1] = pl.full_counts[2];
+    p.full_counts[2] = pl.full_counts[3];
+    p.full_chunk_bytes = pl.full_chunk_bytes;
+    p.max_chunk_bytes = pl.max_chunk_bytes;
+    p.sample_rate = sample_rate;
+    p.raw_chunk_mode = raw_chunk_mode;
+    p.n_streams = n_streams;
+    job->streams.resize(n_streams);
+    bool any_full = false;
+    for (uint32_t i = 0; i < n_streams; i++) {
+        EncStream &e = job->streams[i];
+        memset(&e, 0, sizeof(e));
+        e.pcm_off = pcm_offsets[i];
+        e.out_off = out_offsets[i];
+        e.n_frames = n_frames[i];
+        if (n_frames[i] >= pl.N) any_full = true;
+        const uint32_t last = n_frames[i] % pl.N;
+        if (pl.vbr && last) {
+            uint64_t counts[4];
+            const uint64_t sortable = ((uint64_t)last * channels) / pl.F;  // trap T14
+            vbr_distribution(sortable, pl.vbr_target, counts);
+            e.last_counts[0] = (uint32_t)counts[0];
+            e.last_counts[1] = (uint32_t)counts[2];
+            e.last_counts[2] = (uint32_t)counts[3];
+            if ((counts[0] && pl.base < 2) || (counts[2] && pl.base + 1 > 8) || (counts[3] && pl.base + 2 > 8))
+                return fail(ctx, SEA_B200_ERR_DOMAIN, "VBR bitrate produces a residual size outside 1..8 (common.rs:34 panics)");
+        }
+    }
+    if (any_full && !pl.full_chunk_valid)
+        return fail(ctx, SEA_B200_ERR_DOMAIN, "VBR bitrate produces a residual size outside 1..8 (common.rs:34 panics)");
+    return SEA_B200_OK;
+}
+
+int run_encode(sea_b200_ctx *ctx, EncodeJob &job, const int16_t *d_pcm, uint8_t *d_out, int32_t *d_state, uint64_t *h_out_lens,
+               uint32_t *h_chunk0)
+{
+    const uint32_t n = job.params.n_streams;
+    if (n == 0) return SEA_B200_OK;
+    CU(ctx->streams.reserve(sizeof(EncStream) * n));
+    CU(ctx->lens.reserve(sizeof(uint64_t) * n));
+    CU(ctx->chunk0.reserve(sizeof(uint32_t) * n));
+    EncWorkspace ws = {};
+    ws.vbr_scratch_stride = enc_vbr_scratch_bytes(job.params);
+    if (ws.vbr_scratch_stride) {
+        CU(ctx->scratch.reserve(ws.vbr_scratch_stride * n));
+        ws.vbr_scratch = ctx->scratch.as<uint8_t>();
+    }
+    CU(cudaMemcpyAsync(ctx->streams.p, job.streams.data(), sizeof(EncStream) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ties, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(launch_encode_generic(d_pcm, d_out, ctx->streams.as<EncStream>(), job.params, ctx->tabs, d_state, ctx->lens.as<uint64_t>(),
+                             ctx->chunk0.as<uint32_t>(), ctx->d_ties, ws, ctx->d_err, ctx->stream));
+    ctx->launches++;
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    int dev_err = 0;
+    CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->last_ties, ctx->d_ties, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h_out_lens, ctx->lens.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_chunk0) CU(cudaMemcpyAsync(h_chunk0, ctx->chunk0.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return map_dev_error(ctx, dev_err);
+}
+
+uint64_t encode_bound_bytes(const EncodePlan &pl, uint64_t n_frames)
+{
+    const uint64_t full = n_frames / pl.N, rem = n_frames % pl.N;
+    uint64_t bytes = kFileHeaderBytes + full * pl.full_chunk_bytes;
+    if (rem) {
+        const uint64_t items = (rem + pl.F - 1) / pl.F * pl.channels;
+        const uint64_t bits = pl.vbr ? pl.base + 2 : pl.hdr_bits;
+        bytes += 4 + 16ull * pl.channels + (items * pl.s + 7) / 8 + (pl.vbr ? (items * 2 + 7) / 8 : 0) + (rem * pl.channels * bits + 7) / 8;
+    }
+    return bytes;
+}
+
+}  // namespace
+
+// =================================================================================================== C-ABI
+
+extern "C" {
+
+int sea_b200_abi_version(void) { return SEA_B200_ABI_VERSION; }
+
+const char *sea_b200_strerror(int status)
+{
+    switch (status) {
+        case SEA_B200_OK: return "ok";
+        case SEA_B200_ERR_READ: return "ReadError";
+        case SEA_B200_ERR_INVALID_PARAMETERS: return "InvalidParameters";
+        case SEA_B200_ERR_INVALID_FILE: return "InvalidFile";
+        case SEA_B200_ERR_INVALID_FRAME: return "InvalidFrame";
+        case SEA_B200_ERR_ENCODER_CLOSED: return "EncoderClosed";
+        case SEA_B200_ERR_UNSUPPORTED_VERSION: return "UnsupportedVersion";
+        case SEA_B200_ERR_TOO_MANY_FRAMES: return "TooManyFrames";
+        case SEA_B200_ERR_METADATA_TOO_LARGE: return "MetadataTooLarge";
+        case SEA_B200_ERR_IO: return "IoError";
+        case SEA_B200_ERR_CAPACITY: return "output buffer too small";
+        case SEA_B200_ERR_DOMAIN: return "input outside the reference's domain (the reference panics)";
+        case SEA_B200_ERR_CUDA: return "CUDA failure";
+        case SEA_B200_ERR_NOMEM: return "out of device memory";
+        default: return "unknown";
+    }
+}
+
+int sea_b200_ctx_create(int device, sea_b200_ctx **out)
+{
+    if (!out) return SEA_B200_ERR_INVALID_PARAMETERS;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return SEA_B200_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return SEA_B200_ERR_CUDA;
+    sea_b200_ctx *ctx = new sea_b200_ctx();
+    ctx->device = device;
+    auto bail = [&](cudaError_t) {
+        sea_b200_ctx_destroy(ctx);
+        return SEA_B200_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    ctx->own_stream = true;
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_ties, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
+    for (uint32_t s = 1; s <= 8; s++) {  // SeaDequantTab::init for every scale_factor_bits a chunk header can name
+        std::vector<int32_t> t = build_tables(s);
+        if ((e = cudaMalloc(&ctx->d_tab[s], t.size() * sizeof(int32_t))) != cudaSuccess) return bail(e);
+        if ((e = cudaMemcpy(ctx->d_tab[s], t.data(), t.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+        ctx->tabs.by_s[s] = ctx->d_tab[s];
+    }
+    ctx->tabs.by_s[0] = nullptr;
+    *out = ctx;
+    return SEA_B200_OK;
+}
+
+void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < 9; s++)
+        if (ctx->d_tab[s]) cudaFree(ctx->d_tab[s]);
+    ctx->in.release();
+    ctx->out.release();
+    ctx->streams.release();
+    ctx->lens.release();
+    ctx->chunk0.release();
+    ctx->scratch.release();
+    ctx->misc.release();
+    if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->d_ties) cudaFree(ctx->d_ties);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sea_b200_ctx_set_stream(sea_b200_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return SEA_B200_OK;
+}
+
+void *sea_b200_ctx_stream(const sea_b200_ctx *ctx) { return ctx ? reinterpret_cast<void *>(ctx->stream) : nullptr; }
+const char *sea_b200_last_error(const sea_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t sea_b200_ctx_launch_count(const sea_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+double sea_b200_last_kernel_ms(const sea_b200_ctx *ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+uint64_t sea_b200_last_vbr_ties(const sea_b200_ctx *ctx) { return ctx ? ctx->last_ties : 0; }
+
+void *sea_b200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void sea_b200_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void sea_b200_default_settings(sea_b200_settings *s)
+{
+    memset(s, 0, sizeof(*s));
+    s->frames_per_chunk = 5120;
+    s->scale_factor_bits = 4;
+    s->scale_factor_frames = 20;
+    s->residual_bits = 3.0f;
+    s->vbr = 0;
+}
+
+int sea_b200_parse_header(const uint8_t *sea, uint64_t len, sea_b200_header *out)
+{
+    if (!sea || !out) return SEA_B200_ERR_INVALID_PARAMETERS;
+    return parse_file_header(sea, len, out);
+}
+
+int sea_b200_encode_bound(uint64_t n_frames, uint32_t channels, const sea_b200_settings *s, uint64_t *bytes)
+{
+    EncodePlan pl;
+    int rc = make_encode_plan(channels, s, &pl);
+    if (rc) return rc;
+    *bytes = encode_bound_bytes(pl, n_frames);
+    return SEA_B200_OK;
+}
+
+int sea_b200_full_chunk_bytes(uint32_t channels, const sea_b200_settings *s, uint32_t *bytes)
+{
+    EncodePlan pl;
+    int rc = make_encode_plan(channels, s, &pl);
+    if (rc) return rc;
+    if (!pl.full_chunk_valid) return SEA_B200_ERR_DOMAIN;
+    *bytes = pl.full_chunk_bytes;
+    return SEA_B200_OK;
+}
+
+int sea_b200_vbr_plan(const sea_b200_settings *s, uint64_t sortable_items, float *target, uint32_t *base, uint64_t counts[4])
+{
+    if (!s || s->frames_per_chunk == 0 || s->scale_factor_frames == 0) return SEA_B200_ERR_INVALID_PARAMETERS;
+    const float t = vbr_normalized_bitrate(s);
+    if (target) *target = t;
+    if (base) *base = !(t > 0.0f) ? 0u : (t >= 255.0f ? 255u : (uint32_t)t);
+    if (counts) vbr_distribution(sortable_items, t, counts);
+    return SEA_B200_OK;
+}
+
+int sea_b200_tables(uint32_t residual_bits, uint32_t scale_factor_bits, int32_t *recip, int32_t *dqt)
+{
+    if (residual_bits < 1 || residual_bits > 8 || scale_factor_bits < 1 || scale_factor_bits > 8) return SEA_B200_ERR_INVALID_PARAMETERS;
+    std::vector<int32_t> t = build_tables(scale_factor_bits);
+    const uint32_t n = 1u << scale_factor_bits;
+    if (recip) memcpy(recip, t.data() + tab_recip_off(scale_factor_bits, residual_bits), n * sizeof(int32_t));
+    if (dqt) memcpy(dqt, t.data() + tab_dqt_off(scale_factor_bits, residual_bits), ((size_t)n << residual_bits) * sizeof(int32_t));
+    return SEA_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decode entry points
+
+int sea_b200_decode_batch_device(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *d_sea, const uint64_t *sea_offsets,
+                                 const uint64_t *sea_lens, const uint8_t *headers, int16_t *d_pcm, const uint64_t *pcm_offsets,
+                                 const uint64_t *pcm_caps, uint64_t *n_samples)
+{
+    if (!ctx || !sea_offsets || !sea_lens || !headers || !pcm_offsets) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (n_streams == 0) return SEA_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    DecodeJob job;
+    int rc = plan_decode(ctx, n_streams, headers, kFileHeaderBytes, sea_offsets, sea_lens, pcm_offsets, pcm_caps, &job);
+    if (rc) return rc;
+    uint64_t sea_len = 0;
+    for (uint32_t i = 0; i < n_streams; i++) sea_len = std::max(sea_len, sea_offsets[i] + sea_lens[i]);
+    // the first chunk's header word picks the specialised kernel; fetch it from the device copy
+    uint32_t hdr_word = 0;
+    bool have = false;
+    if (job.streams[0].n_chunks > 0 && job.streams[0].data_len >= 4) {
+        uint8_t w[4];
+        CU(cudaMemcpyAsync(w, d_sea + job.streams[0].data_off, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
+        have = true;
+    }
+    rc = run_decode(ctx, job, d_sea, sea_len, d_pcm, have, hdr_word);
+    if (n_samples)
+        for (uint32_t i = 0; i < n_streams; i++) n_samples[i] = rc == SEA_B200_OK ? job.n_samples[i] : 0;
+    if (rc == SEA_B200_OK && job.trailing_invalid_frame)
+        return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "streaming header with a short last chunk (chunk.rs:76-79)");
+    return rc;
+}
+
+int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *sea, const uint64_t *sea_offsets,
+                          const uint64_t *sea_lens, int16_t *pcm, const uint64_t *pcm_offsets, const uint64_t *pcm_caps,
+                          uint64_t *n_samples)
+{
+    if (!ctx || !sea || !sea_offsets || !sea_lens || !pcm_offsets) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (n_streams == 0) return SEA_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    // host copy of the headers, and the byte range to ship
+    std::vector<uint8_t> headers((size_t)n_streams * kFileHeaderBytes, 0);
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (uint32_t i = 0; i < n_streams; i++) {
+        memcpy(&headers[(size_t)i * kFileHeaderBytes], sea + sea_offsets[i], (size_t)std::min<uint64_t>(sea_lens[i], kFileHeaderBytes));
+        lo = std::min(lo, sea_offsets[i]);
+        hi = std::max(hi, sea_offsets[i] + sea_lens[i]);
+    }
+    std::vector<uint64_t> rel_off(n_streams);
+    for (uint32_t i = 0; i < n_streams; i++) rel_off[i] = sea_offsets[i] - lo;
+    DecodeJob job;
+    int rc = plan_decode(ctx, n_streams, headers.data(), kFileHeaderBytes, rel_off.data(), sea_lens, pcm_offsets, pcm_caps, &job);
+    if (rc) return rc;
+    uint64_t plo = UINT64_MAX, phi = 0;
+    for (uint32_t i = 0; i < n_streams; i++) {
+        if (job.n_samples[i] == 0) continue;
+        plo = std::min(plo, pcm_offsets[i]);
+        phi = std::max(phi, pcm_offsets[i] + job.n_samples[i]);
+    }
+    if (phi == 0) plo = 0;
+    if (phi && !pcm) return SEA_B200_ERR_INVALID_PARAMETERS;
+    for (auto &d : job.streams) d.pcm_off -= plo;
+    const uint64_t in_bytes = hi - lo, out_samples = phi - plo;
+    CU(ctx->in.reserve(in_bytes + 64));
+    CU(ctx->out.reserve(out_samples * 2 + 64));
+    CU(cudaMemcpyAsync(ctx->in.p, sea + lo, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t hdr_word = 0;
+    bool have = false;
+    if (job.streams[0].n_chunks > 0 && job.streams[0].data_len >= 4) {
+        const uint8_t *w = sea + sea_offsets[0] + kFileHeaderBytes;
+        hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
+        have = true;
+    }
+    rc = run_decode(ctx, job, ctx->in.as<uint8_t>(), in_bytes, ctx->out.as<int16_t>(), have, hdr_word);
+    if (rc == SEA_B200_OK && out_samples) {
+        CU(cudaMemcpyAsync(pcm + plo, ctx->out.p, out_samples * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_samples)
+        for (uint32_t i = 0; i < n_streams; i++) n_samples[i] = rc == SEA_B200_OK ? job.n_samples[i] : 0;
+    if (rc == SEA_B200_OK && job.trailing_invalid_frame)
+        return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "streaming header with a short last chunk (chunk.rs:76-79)");
+    return rc;
+}
+
+int sea_b200_decode(sea_b200_ctx *ctx, const uint8_t *sea, uint64_t len, int16_t *pcm, uint64_t pcm_cap_samples, uint64_t *n_samples,
+                    uint32_t *sample_rate, uint32_t *channels)
+{
+    if (!ctx || !sea) return SEA_B200_ERR_INVALID_PARAMETERS;
+    sea_b200_header h;
+    int rc = parse_file_header(sea, len, &h);
+    if (rc) return fail(ctx, rc, "bad .sea header (file.rs:40-72)");
+    if (sample_rate) *sample_rate = h.sample_rate;
+    if (channels) *channels = h.channels;
+    const uint64_t off = 0, poff = 0;
+    if (!pcm) {  // c/sea.h:209-211 two-call pattern: report the size only
+        DecodeJob job;
+        rc = plan_decode(ctx, 1, sea, kFileHeaderBytes, &off, &len, &poff, nullptr, &job);
+        if (rc) return rc;
+        if (n_samples) *n_samples = job.n_samples[0];
+        return SEA_B200_OK;
+    }
+    return sea_b200_decode_batch(ctx, 1, sea, &off, &len, pcm, &poff, &pcm_cap_samples, n_samples);
+}
+
+// ------------------------------------------------------------------------------------------------ encode entry points
+
+int sea_b200_encode_batch_device(sea_b200_ctx *ctx, uint32_t n_streams, const int16_t *d_pcm, const uint64_t *pcm_offsets,
+                                 const uint32_t *n_frames, uint32_t sample_rate, uint32_t channels, const sea_b200_settings *settings,
+                                 uint8_t *d_out, const uint64_t *out_offsets, uint64_t *out_lens)
+{
+    if (!ctx || !pcm_offsets || !n_frames || !settings || !out_offsets || !out_lens) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (n_streams == 0) return SEA_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    EncodeJob job;
+    int rc = plan_encode(ctx, n_streams, pcm_offsets, n_frames, sample_rate, channels, settings, out_offsets, false, &job);
+    if (rc) return rc;
+    return run_encode(ctx, job, d_pcm, d_out, nullptr, out_lens, nullptr);
+}
+
+int sea_b200_encode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const int16_t *pcm, const uint64_t *pcm_offsets, const uint32_t *n_frames,
+                          uint32_t sample_rate, uint32_t channels, const sea_b200_settings *settings, uint8_t *out,
+                          const uint64_t *out_offsets, uint64_t *out_lens)
+{
+    if (!ctx || !pcm_offsets || !n_frames || !settings || !out || !out_offsets || !out_lens) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (n_streams == 0) return SEA_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    EncodeJob job;
+    int rc = plan_encode(ctx, n_streams, pcm_offsets, n_frames, sample_rate, channels, settings, out_offsets, false, &job);
+    if (rc) return rc;
+    uint64_t lo = UINT64_MAX, hi = 0, olo = UINT64_MAX, ohi = 0;
+    for (uint32_t i = 0; i < n_streams; i++) {
+        const uint64_t ns = (uint64_t)n_frames[i] * channels;
+        if (ns) {
+            lo = std::min(lo, pcm_offsets[i]);
+            hi = std::max(hi, pcm_offsets[i] + ns);
+        }
+        olo = std::min(olo, out_offsets[i]);
+        ohi = std::max(ohi, out_offsets[i] + encode_bound_bytes(job.plan, n_frames[i]));
+    }
+    if (hi == 0) lo = 0;
+    if (hi && !pcm) return SEA_B200_ERR_INVALID_PARAMETERS;
+    for (auto &e : job.streams) {
+        e.pcm_off -= (e.n_frames ? lo : e.pcm_off);
+        e.out_off -= olo;
+    }
+    CU(ctx->in.reserve((hi - lo) * 2 + 64));
+    CU(ctx->out.reserve(ohi - olo + 64));
+    if (hi) CU(cudaMemcpyAsync(ctx->in.p, pcm + lo, (hi - lo) * 2, cudaMemcpyHostToDevice, ctx->stream));
+    rc = run_encode(ctx, job, ctx->in.as<int16_t>(), ctx->out.as<uint8_t>(), nullptr, out_lens, nullptr);
+    if (rc) return rc;
+    // ship back only what was written
+    uint64_t wlo = UINT64_MAX, whi = 0;
+    for (uint32_t i = 0; i < n_streams; i++) {
+        wlo = std::min(wlo, out_offsets[i]);
+        whi = std::max(whi, out_offsets[i] + out_lens[i]);
+    }
+    CU(cudaMemcpyAsync(out + wlo, ctx->out.as<uint8_t>() + (wlo - olo), whi - wlo, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SEA_B200_OK;
+}
+
+int sea_b200_encode(sea_b200_ctx *ctx, const int16_t *pcm, uint64_t n_samples, uint32_t sample_rate, uint32_t channels,
+                    const sea_b200_settings *settings, uint8_t *out, uint64_t out_cap, uint64_t *out_len)
+{
+    if (!ctx || !settings || !out || !out_len || channels == 0) return SEA_B200_ERR_INVALID_PARAMETERS;
+    const uint64_t frames64 = n_samples / channels;  // lib.rs:25 (`as u32`)
+    if (frames64 > 0xffffffffull) return fail(ctx, SEA_B200_ERR_TOO_MANY_FRAMES, "more than 2^32 frames");
+    if (frames64 == 0 && n_samples != 0)
+        return fail(ctx, SEA_B200_ERR_DOMAIN, "fewer samples than channels: the reference fails with UnexpectedEof (encoder.rs:95-99)");
+    const uint32_t frames = (uint32_t)frames64;
+    uint64_t bound = 0;
+    int rc = sea_b200_encode_bound(frames, channels, settings, &bound);
+    if (rc) return fail(ctx, rc, "encoder settings rejected (outside the reference's domain)");
+    if (bound > out_cap) return fail(ctx, SEA_B200_ERR_CAPACITY, "output buffer smaller than sea_b200_encode_bound");
+    const uint64_t off = 0;
+    return sea_b200_encode_batch(ctx, 1, pcm, &off, &frames, sample_rate, channels, settings, out, &off, out_len);
+}
+
+// ------------------------------------------------------------------------------------------------ streaming seam
+
+int sea_b200_encoder_create(sea_b200_ctx *ctx, uint32_t channels, uint32_t sample_rate, const sea_b200_settings *settings,
+                            sea_b200_encoder **out)
+{
+    if (!ctx || !settings || !out) return SEA_B200_ERR_INVALID_PARAMETERS;
+    *out = nullptr;
+    EncodePlan pl;
+    int rc = make_encode_plan(channels, settings, &pl);
+    if (rc) return fail(ctx, rc, "encoder settings rejected (outside the reference's domain)");
+    CU(cudaSetDevice(ctx->device));
+    sea_b200_encoder *enc = new sea_b200_encoder();
+    enc->ctx = ctx;
+    enc->settings = *settings;
+    enc->plan = pl;
+    enc->channels = channels;
+    enc->sample_rate = sample_rate;
+    std::vector<int32_t> init((size_t)channels * kEncStateWords, 0);
+    for (uint32_t c = 0; c < channels; c++) {  // lms.rs:19-32
+        init[(size_t)c * kEncStateWords + 4 + 2] = -(1 << 13);
+        init[(size_t)c * kEncStateWords + 4 + 3] = 1 << 14;
+    }
+    cudaError_t e = cudaMalloc(&enc->d_state, init.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(enc->d_state, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (enc->d_state) cudaFree(enc->d_state);
+        delete enc;
+        return cuda_fail(ctx, e, "encoder state");
+    }
+    *out = enc;
+    return SEA_B200_OK;
+}
+
+uint32_t sea_b200_encoder_chunk_size(const sea_b200_encoder *enc) { return enc ? enc->chunk_size : 0; }
+
+void sea_b200_encoder_destroy(sea_b200_encoder *enc)
+{
+    if (!enc) return;
+    cudaSetDevice(enc->ctx->device);
+    if (enc->d_state) cudaFree(enc->d_state);
+    delete enc;
+}
+
+int sea_b200_encoder_make_chunk(sea_b200_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint8_t *out, uint64_t out_cap,
+                                uint64_t *out_len)
+{
+    if (!enc || !pcm || !out || !out_len) return SEA_B200_ERR_INVALID_PARAMETERS;
+    sea_b200_ctx *ctx = enc->ctx;
+    const EncodePlan &pl = enc->plan;
+    if (n_samples == 0 || n_samples % enc->channels) return fail(ctx, SEA_B200_ERR_INVALID_PARAMETERS, "make_chunk needs whole frames");
+    const uint64_t frames64 = n_samples / enc->channels;
+    if (frames64 > pl.N) return fail(ctx, SEA_B200_ERR_DOMAIN, "more than frames_per_chunk frames (file.rs:173-175 assert)");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t frames = (uint32_t)frames64;
+    const uint64_t zero = 0;
+    EncodeJob job;
+    int rc = plan_encode(ctx, 1, &zero, &frames, enc->sample_rate, enc->channels, &enc->settings, &zero, true, &job);
+    if (rc) return rc;
+    CU(ctx->in.reserve(n_samples * 2 + 64));
+    CU(ctx->out.reserve(pl.max_chunk_bytes + 64));
+    CU(cudaMemcpyAsync(ctx->in.p, pcm, n_samples * 2, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t len = 0;
+    rc = run_encode(ctx, job, ctx->in.as<int16_t>(), ctx->out.as<uint8_t>(), enc->d_state, &len, nullptr);
+    if (rc) return rc;
+    if (len > out_cap) return fail(ctx, SEA_B200_ERR_CAPACITY, "chunk buffer too small");
+    CU(cudaMemcpyAsync(out, ctx->out.p, len, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (enc->chunk_size == 0) enc->chunk_size = (uint32_t)len & 0xffffu;  // file.rs:166-168 (`as u16`)
+    if (frames == pl.N && enc->chunk_size != ((uint32_t)len & 0xffffu))
+        return fail(ctx, SEA_B200_ERR_DOMAIN, "full chunk size differs from header.chunk_size (file.rs:173-175 assert)");
+    *out_len = len;
+    return SEA_B200_OK;
+}
+
+int sea_b200_decoder_create(sea_b200_ctx *ctx, const uint8_t *header22, uint64_t len, sea_b200_decoder **out)
+{
+    if (!ctx || !header22 || !out) return SEA_B200_ERR_INVALID_PARAMETERS;
+    *out = nullptr;
+    sea_b200_header h;
+    int rc = parse_file_header(header22, len, &h);
+    if (rc) return fail(ctx, rc, "bad .sea header (file.rs:40-72)");
+    sea_b200_decoder *dec = new sea_b200_decoder();
+    dec->ctx = ctx;
+    dec->header = h;
+    *out = dec;
+    return SEA_B200_OK;
+}
+
+int sea_b200_decoder_header(const sea_b200_decoder *dec, sea_b200_header *out)
+{
+    if (!dec || !out) return SEA_B200_ERR_INVALID_PARAMETERS;
+    *out = dec->header;
+    return SEA_B200_OK;
+}
+
+void sea_b200_decoder_destroy(sea_b200_decoder *dec) { delete dec; }
+
+int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, uint64_t len, int64_t remaining_frames, int16_t *pcm,
+                                  uint64_t pcm_cap_samples, uint64_t *n_samples)
+{
+    if (!dec || !chunk || !pcm || !n_samples) return SEA_B200_ERR_INVALID_PARAMETERS;
+    sea_b200_ctx *ctx = dec->ctx;
+    const sea_b200_header &h = dec->header;
+    *n_samples = 0;
+    if (len == 0) return fail(ctx, SEA_B200_ERR_INVALID_PARAMETERS, "empty chunk (samples_from_reader returns None before parsing)");
+    if (len > h.chunk_size) return fail(ctx, SEA_B200_ERR_DOMAIN, "chunk longer than header.chunk_size (chunk.rs:74 assert)");
+    if (remaining_frames < 0 && len < h.chunk_size) return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "short chunk in streaming mode (chunk.rs:76-79)");
+    if (len < 4) return fail(ctx, SEA_B200_ERR_DOMAIN, "chunk shorter than its header");
+    if (chunk[0] != 1 && chunk[0] != 2) return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "chunk type is neither CBR nor VBR (chunk.rs:81-85)");
+    const int sfb = chunk[1] >> 4;
+    if (dec->sf_bits < 0) dec->sf_bits = sfb;
+    else if (dec->sf_bits != sfb) return fail(ctx, SEA_B200_ERR_DOMAIN, "scale_factor_bits changed between chunks (decoder.rs:21 assert)");
+    uint64_t frames = h.frames_per_chunk;
+    if (remaining_frames >= 0 && (uint64_t)remaining_frames < frames) frames = (uint64_t)remaining_frames;
+    if (frames == 0) return SEA_B200_OK;
+    if (frames * h.channels > pcm_cap_samples) return fail(ctx, SEA_B200_ERR_CAPACITY, "PCM buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    DecodeJob job;
+    job.streams.resize(1);
+    job.n_samples.assign(1, frames * h.channels);
+    DecStream &d = job.streams[0];
+    memset(&d, 0, sizeof(d));
+    d.data_off = 0;
+    d.data_len = len;
+    d.pcm_off = 0;
+    d.total_frames = (uint32_t)frames;
+    d.n_chunks = 1;
+    d.chain_begin = 0;
+    d.chunk_size = h.chunk_size;
+    d.frames_per_chunk = h.frames_per_chunk;
+    d.channels = h.channels;
+    job.total_chains = h.channels;
+    job.first = h;
+    job.uniform = false;  // one chunk: the generic kernel is the latency path
+    CU(ctx->in.reserve(len + 64));
+    CU(ctx->out.reserve(frames * h.channels * 2 + 64));
+    CU(cudaMemcpyAsync(ctx->in.p, chunk, len, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = run_decode(ctx, job, ctx->in.as<uint8_t>(), len, ctx->out.as<int16_t>(), false, 0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pcm, ctx->out.p, frames * h.channels * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n_samples = frames * h.channels;
+    return SEA_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+
+int sea_b200_int32_peak(sea_b200_ctx *ctx, int mode, double *ops_per_s, double *ms_out)
+{
+    if (!ctx || mode < 0 || mode > 2) return SEA_B200_ERR_INVALID_PARAMETERS;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->misc.reserve(256));
+    uint64_t lane_ops = 0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        CU(launch_int32_peak(mode, ctx->misc.as<uint32_t>(), &lane_ops, ctx->stream));
+        ctx->launches++;
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    if (ms_out) *ms_out = best;
+    if (ops_per_s) *ops_per_s = (double)lane_ops / ((double)best * 1e-3);
+    return SEA_B200_OK;
+}
+
+}  // extern "C"

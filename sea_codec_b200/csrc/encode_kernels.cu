@@ -1,0 +1,417 @@
+// encode_kernels.cu -- SEA encoder for sm_100a: scale-factor search, VBR allocation and bit packing on the device.
+//
+// Replaces EncoderBase::{calculate_residuals, get_residuals_with_best_scalefactor, get_residuals_for_chunk}
+// (encoder_base.rs:44-195), CbrEncoder::encode (encoder_cbr.rs:36-66), VbrEncoder::{analyze,
+// choose_residual_len_from_errors, encode} (encoder_vbr.rs:98-214), BitPacker (bits.rs:89-135) and
+// SeaChunk::serialize (chunk.rs:215-292).
+//
+// A stream cannot be split by chunk: the LMS state and prev_scalefactor carry over (encoder_base.rs:181-182).
+// One CTA owns one stream.  Within it a chain = one channel; the 2^s scale-factor candidates of a block are
+// evaluated by the lanes of a chain group in lock step (no early exit: an aborted candidate can never win,
+// SURVEY trap T4), a shuffle arg-min on the key (rank, (sf - prev_sf) mod 2^s) picks what the sequential
+// reference loop would have kept (trap T1), and the winner's state is written back before the next block.
+// The serialized chunk is assembled in shared memory as a big-endian bit string and written out per chunk.
+#include "sea_kernels.h"
+
+namespace sea {
+
+__device__ __forceinline__ void enc_report(int *err, int code) { atomicCAS(err, 0, code); }
+
+// OR an n <= 8 bit field into the big-endian word view of the chunk at absolute bit position pos.
+__device__ __forceinline__ void put_bits(uint32_t *buf, uint32_t pos, uint32_t n, uint32_t value)
+{
+    const uint32_t word = pos >> 5, off = pos & 31u;
+    if (off + n <= 32u) {
+        atomicOr(&buf[word], value << (32u - off - n));
+    } else {
+        const uint32_t spill = off + n - 32u;
+        atomicOr(&buf[word], value >> spill);
+        atomicOr(&buf[word + 1], value << (32u - spill));
+    }
+}
+__device__ __forceinline__ void put_byte(uint32_t *buf, uint32_t byte_off, uint32_t v) { put_bits(buf, byte_off * 8u, 8u, v & 0xffu); }
+
+struct VbrScratch {
+    unsigned long long *keys;  // ranks, then sort keys           [npow2]
+    uint32_t *idx;             // item index per sorted position   [npow2]
+    uint32_t *blkbit;          // bit offset of each block         [nblk]
+    uint32_t *rowbits;         // bits per frame of each block     [nblk]
+    uint8_t *sizes;            // residual size per (block, channel)
+};
+
+static __host__ __device__ inline uint32_t next_pow2(uint32_t v)
+{
+    uint32_t p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+uint64_t enc_vbr_scratch_bytes(const EncParams &p)
+{
+    if (!p.vbr) return 0;
+    const uint64_t nblk = p.N / p.F, items = nblk * p.channels, np2 = next_pow2((uint32_t)items);
+    uint64_t bytes = np2 * 8 + np2 * 4 + nblk * 4 + nblk * 4 + items;
+    return (bytes + 255) & ~(uint64_t)255;
+}
+
+__device__ __forceinline__ VbrScratch carve_scratch(uint8_t *base, const EncParams &p)
+{
+    const uint32_t nblk = p.N / p.F, items = nblk * p.channels, np2 = next_pow2(items);
+    VbrScratch v;
+    v.keys = reinterpret_cast<unsigned long long *>(base);
+    v.idx = reinterpret_cast<uint32_t *>(base + (uint64_t)np2 * 8);
+    v.blkbit = v.idx + np2;
+    v.rowbits = v.blkbit + nblk;
+    v.sizes = reinterpret_cast<uint8_t *>(v.rowbits + nblk);
+    return v;
+}
+
+// One search pass over a chunk (CBR encode, VBR analysis, or VBR encode).  Warps advance independently: a chain
+// only depends on its own history.  mode: 0 = encode with uniform size, 1 = analysis (ranks only), 2 = encode with
+// per-(block, channel) sizes.
+__device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p, const int16_t *__restrict__ x0, uint32_t frames,
+                            const int32_t *__restrict__ tab, int32_t *st_w, int32_t *st_h, int32_t *st_prev, uint8_t *codes,
+                            uint32_t *chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs)
+{
+    const uint32_t C = p.channels, F = p.F, s = p.s, nsf = 1u << s;
+    const uint32_t lpc = nsf < 32u ? nsf : 32u;  // lanes per chain group
+    const uint32_t cpw = 32u / lpc;              // chain groups per warp
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t grp = lane / lpc, lic = lane % lpc;
+    const uint32_t slots = nwarps * cpw;
+    const uint32_t T = blockDim.x;
+    const uint32_t nblk = div_ceil_u32(frames, F);
+
+    for (uint32_t blk = 0; blk < nblk; blk++) {
+        uint32_t nf = frames - blk * F;
+        if (nf > F) nf = F;
+        for (uint32_t cb = warp * cpw; cb < C; cb += slots) {  // warp-uniform trip count
+            const uint32_t c_raw = cb + grp;
+            const bool active = c_raw < C;
+            const uint32_t c = active ? c_raw : C - 1u;
+            const uint32_t size = mode == 2 ? vs.sizes[blk * C + c] : uniform_size;
+            const int32_t *recips = tab + tab_recip_off(s, size);
+            const int32_t *rows = tab + tab_dqt_off(s, size);
+            const int16_t *x = x0 + (uint64_t)blk * F * C + c;
+
+            int32_t rw[4], rh[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                rw[i] = st_w[c * 4 + i];
+                rh[i] = st_h[c * 4 + i];
+            }
+            const uint32_t prev = (uint32_t)st_prev[c];
+
+            unsigned long long best_rank = ~0ull;
+            uint32_t best_ord = 0xffffffffu, best_sf = 0, best_buf = 0, cur_buf = 0;
+            int32_t bw[4] = {0, 0, 0, 0}, bh[4] = {0, 0, 0, 0};
+            for (uint32_t sf = lic; sf < nsf; sf += lpc) {
+                const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
+                const int32_t recip = __ldg(recips + sf);
+                const int32_t *row = rows + (sf << size);
+                int32_t w[4], h[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    w[i] = rw[i];
+                    h[i] = rh[i];
+                }
+                unsigned long long rank = 0;
+                uint8_t *cbuf = codes + (size_t)cur_buf * F * T + threadIdx.x;
+                for (uint32_t f = 0; f < nf; f++) {  // encoder_base.rs:64-89
+                    const int32_t xs = __ldg(x + (uint64_t)f * C);
+                    const int32_t pr = lms_predict(w, h);
+                    const int32_t r = (int32_t)((uint32_t)xs - (uint32_t)pr);
+                    const uint32_t code = quant_code(r, recip, size);
+                    const int32_t d = __ldg(row + code);
+                    const int32_t y = clamp_i16((int32_t)((uint32_t)pr + (uint32_t)d));
+                    const int32_t e = xs - y;
+                    rank += (unsigned long long)((long long)e * e) + lms_penalty(w);
+                    lms_update(w, h, y, d);
+                    cbuf[(size_t)f * T] = (uint8_t)code;
+                }
+                if (rank < best_rank || (rank == best_rank && ord < best_ord)) {
+                    best_rank = rank;
+                    best_ord = ord;
+                    best_sf = sf;
+                    best_buf = cur_buf;
+                    cur_buf ^= 1u;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        bw[i] = w[i];
+                        bh[i] = h[i];
+                    }
+                }
+            }
+            // arg-min over the chain group: strict total order (rank, ord) -> every lane agrees on the winner
+            unsigned long long g_rank = best_rank;
+            uint32_t g_ord = best_ord, g_lane = lane, g_buf = best_buf;
+            for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
+                const unsigned long long o_rank = __shfl_xor_sync(0xffffffffu, g_rank, o);
+                const uint32_t o_ord = __shfl_xor_sync(0xffffffffu, g_ord, o);
+                const uint32_t o_lane = __shfl_xor_sync(0xffffffffu, g_lane, o);
+                const uint32_t o_buf = __shfl_xor_sync(0xffffffffu, g_buf, o);
+                if (o_rank < g_rank || (o_rank == g_rank && o_ord < g_ord)) {
+                    g_rank = o_rank;
+                    g_ord = o_ord;
+                    g_lane = o_lane;
+                    g_buf = o_buf;
+                }
+            }
+            if (active && lane == g_lane) {  // encoder_base.rs:181-186: persist the winner
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    st_w[c * 4 + i] = bw[i];
+                    st_h[c * 4 + i] = bh[i];
+                }
+                st_prev[c] = (int32_t)best_sf;
+                if (mode == 1) vs.keys[blk * C + c] = best_rank;
+                else put_bits(chunk_buf, sf_sec_bit + (blk * C + c) * s, s, best_sf);
+            }
+            if (mode != 1 && active) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
+                uint32_t blockbit, rowbits, prefix;
+                if (mode == 2) {
+                    blockbit = vs.blkbit[blk];
+                    rowbits = vs.rowbits[blk];
+                    prefix = 0;
+                    for (uint32_t cc = 0; cc < c; cc++) prefix += vs.sizes[blk * C + cc];
+                } else {
+                    rowbits = C * size;
+                    blockbit = blk * F * rowbits;
+                    prefix = c * size;
+                }
+                const uint8_t *wbuf = codes + (size_t)g_buf * F * T + (threadIdx.x - lane + g_lane);
+                for (uint32_t f = lic; f < nf; f += lpc)
+                    put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[(size_t)f * T]);
+            }
+            __syncwarp();  // code buffers are reused by the next chain round
+        }
+    }
+}
+
+// CTA-wide bitonic sort of (key, idx) pairs, ascending; idx breaks ties (SURVEY trap T13).
+__device__ void bitonic_sort(unsigned long long *keys, uint32_t *idx, uint32_t n)
+{
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const unsigned long long ki = keys[i], kl = keys[l];
+                    const uint32_t ii = idx[i], il = idx[l];
+                    const bool gt = ki > kl || (ki == kl && ii > il);
+                    const bool up = (i & k) == 0;
+                    if (gt == up) {
+                        keys[i] = kl;
+                        keys[l] = ki;
+                        idx[i] = il;
+                        idx[l] = ii;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void encode_generic_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out,
+                                      const EncStream *__restrict__ streams, EncParams p, DevTables tabs, int32_t *state,
+                                      uint64_t *out_lens, uint32_t *chunk0, unsigned long long *ties, EncWorkspace ws, int *err)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t sidx = blockIdx.x;
+    const EncStream st = streams[sidx];
+    const uint32_t C = p.channels, N = p.N, F = p.F, s = p.s, T = blockDim.x, tid = threadIdx.x;
+    const int32_t *tab = tabs.by_s[s];
+
+    const uint32_t buf_words = (p.max_chunk_bytes + 3u) / 4u + 2u;
+    uint32_t *chunk_buf = reinterpret_cast<uint32_t *>(smem);
+    int32_t *st_w = reinterpret_cast<int32_t *>(chunk_buf + buf_words);
+    int32_t *st_h = st_w + 4 * C;
+    int32_t *st_prev = st_h + 4 * C;
+    int32_t *sv_w = st_prev + C;
+    int32_t *sv_h = sv_w + 4 * C;
+    uint8_t *codes = reinterpret_cast<uint8_t *>(sv_h + 4 * C);
+    __shared__ uint32_t sh_res_bits;
+
+    VbrScratch vs = {};
+    if (p.vbr) vs = carve_scratch(ws.vbr_scratch + (uint64_t)sidx * ws.vbr_scratch_stride, p);
+
+    // EncoderBase::new (encoder_base.rs:29-41, lms.rs:19-32) or the state kept by a streaming handle
+    for (uint32_t c = tid; c < C; c += T) {
+        if (state) {
+            const int32_t *sp = state + ((uint64_t)sidx * C + c) * kEncStateWords;
+            for (int i = 0; i < 4; i++) {
+                st_h[c * 4 + i] = sp[i];
+                st_w[c * 4 + i] = sp[4 + i];
+            }
+            st_prev[c] = sp[8];
+        } else {
+            for (int i = 0; i < 4; i++) st_h[c * 4 + i] = 0;
+            st_w[c * 4 + 0] = 0;
+            st_w[c * 4 + 1] = 0;
+            st_w[c * 4 + 2] = -(1 << 13);
+            st_w[c * 4 + 3] = 1 << 14;
+            st_prev[c] = 0;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t n_chunks = div_ceil_u32(st.n_frames, N);
+    uint64_t written = p.raw_chunk_mode ? 0 : kFileHeaderBytes;
+    uint32_t first_chunk_bytes = 0;
+
+    for (uint32_t k = 0; k < n_chunks; k++) {
+        uint32_t frames = st.n_frames - k * N;
+        if (frames > N) frames = N;
+        const uint32_t nblk = div_ceil_u32(frames, F), items = nblk * C;
+        const int16_t *x0 = pcm + st.pcm_off + (uint64_t)k * N * C;
+
+        for (uint32_t i = tid; i < buf_words; i += T) chunk_buf[i] = 0;
+        for (uint32_t i = tid; i < 4 * C; i += T) {  // file.rs:146-149: the chunk header carries the LMS *before* the chunk
+            sv_w[i] = st_w[i];
+            sv_h[i] = st_h[i];
+        }
+        __syncthreads();
+
+        const uint32_t sf_sec_bit = (4u + 16u * C) * 8u;
+        const uint32_t vbr_sec_bit = sf_sec_bit + div_ceil_u32(items * s, 8u) * 8u;
+        const uint32_t res_sec_bit = vbr_sec_bit + (p.vbr ? div_ceil_u32(items * 2u, 8u) * 8u : 0u);
+
+        if (tid == 0) {  // chunk.rs:215-226
+            put_byte(chunk_buf, 0, p.vbr ? 2u : 1u);
+            put_byte(chunk_buf, 1, (s << 4) | p.hdr_bits);
+            put_byte(chunk_buf, 2, F);
+            put_byte(chunk_buf, 3, 0x5Au);
+        }
+        for (uint32_t i = tid; i < 4 * C; i += T) {  // lms.rs:64-78: low 16 bits, history then weights, LE
+            const uint32_t c = i >> 2, t = i & 3u;
+            const uint32_t hv = (uint32_t)sv_h[i], wv = (uint32_t)sv_w[i];
+            const uint32_t base_byte = 4u + 16u * c;
+            put_byte(chunk_buf, base_byte + 2u * t, hv);
+            put_byte(chunk_buf, base_byte + 2u * t + 1u, hv >> 8);
+            put_byte(chunk_buf, base_byte + 8u + 2u * t, wv);
+            put_byte(chunk_buf, base_byte + 8u + 2u * t + 1u, wv >> 8);
+        }
+
+        if (!p.vbr) {
+            search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (tid == 0) sh_res_bits = frames * C * p.hdr_bits;
+        } else {
+            // ---- analysis at base+1 bits (encoder_vbr.rs:139-171); restores lms only (trap T2)
+            search_pass(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            __syncthreads();
+            for (uint32_t i = tid; i < 4 * C; i += T) {
+                st_w[i] = sv_w[i];
+                st_h[i] = sv_h[i];
+            }
+            // ---- choose_residual_len_from_errors (encoder_vbr.rs:98-137)
+            const uint32_t sortable = (frames * C) / F;  // trap T14: interleaved sample count / F
+            const bool full = frames == N;
+            const uint32_t m1 = full ? p.full_counts[0] : st.last_counts[0];
+            const uint32_t p1 = full ? p.full_counts[1] : st.last_counts[1];
+            const uint32_t p2 = full ? p.full_counts[2] : st.last_counts[2];
+            const uint32_t np2 = next_pow2(sortable);
+            for (uint32_t i = tid; i < np2; i += T) {
+                if (i >= sortable) vs.keys[i] = ~0ull;
+                vs.idx[i] = i < sortable ? i : 0xffffffffu;
+            }
+            for (uint32_t i = tid; i < items; i += T) vs.sizes[i] = (uint8_t)p.base;
+            __syncthreads();
+            bitonic_sort(vs.keys, vs.idx, np2);
+            for (uint32_t pos = tid; pos < sortable; pos += T) {
+                uint32_t size = p.base;
+                if (pos < m1) size = p.base - 1u;
+                if (pos >= sortable - p2 - p1) size = p.base + 1u;
+                if (pos >= sortable - p2) size = p.base + 2u;
+                if (size < 1u || size > 8u) enc_report(err, kDevDomain);  // SeaResidualSize::from panics (trap T20)
+                vs.sizes[vs.idx[pos]] = (uint8_t)size;
+                const bool boundary = pos > 0 && (pos == m1 || pos == sortable - p2 - p1 || pos == sortable - p2);
+                if (boundary && vs.keys[pos - 1] == vs.keys[pos]) {
+                    uint32_t before = p.base;  // size of position pos-1
+                    if (pos - 1 < m1) before = p.base - 1u;
+                    if (pos - 1 >= sortable - p2 - p1) before = p.base + 1u;
+                    if (pos - 1 >= sortable - p2) before = p.base + 2u;
+                    if (before != size) atomicAdd(ties, 1ull);  // trap T13: tie across a bucket boundary
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {  // bit offset of every block inside the residual section
+                uint32_t acc = 0;
+                for (uint32_t blk = 0; blk < nblk; blk++) {
+                    uint32_t rb = 0;
+                    for (uint32_t c = 0; c < C; c++) rb += vs.sizes[blk * C + c];
+                    uint32_t nf = frames - blk * F;
+                    if (nf > F) nf = F;
+                    vs.blkbit[blk] = acc;
+                    vs.rowbits[blk] = rb;
+                    acc += nf * rb;
+                }
+                sh_res_bits = acc;
+            }
+            for (uint32_t i = tid; i < items; i += T)  // chunk.rs:245-252 (release build masks to 2 bits)
+                put_bits(chunk_buf, vbr_sec_bit + 2u * i, 2u, ((uint32_t)vs.sizes[i] - p.hdr_bits + 1u) & 3u);
+            __syncthreads();
+            // ---- second pass with the chosen sizes (encoder_vbr.rs:193-207)
+            search_pass(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+        }
+        __syncthreads();
+
+        const uint32_t chunk_bytes = res_sec_bit / 8u + (sh_res_bits + 7u) / 8u;
+        if (chunk_bytes > p.max_chunk_bytes) enc_report(err, kDevDomain);
+        uint8_t *dst = out + st.out_off + (p.raw_chunk_mode ? 0 : (uint64_t)kFileHeaderBytes + (uint64_t)k * p.full_chunk_bytes);
+        for (uint32_t i = tid; i < chunk_bytes && i < p.max_chunk_bytes; i += T)
+            dst[i] = (uint8_t)(chunk_buf[i >> 2] >> (24u - 8u * (i & 3u)));
+        if (k == 0) first_chunk_bytes = chunk_bytes;
+        written += chunk_bytes;
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        if (!p.raw_chunk_mode) {  // file.rs:78-93; chunk_size = first chunk (file.rs:166-168); total_frames as u32
+            uint8_t *hd = out + st.out_off;
+            hd[0] = 's'; hd[1] = 'e'; hd[2] = 'a'; hd[3] = 'c';
+            hd[4] = 1;
+            hd[5] = (uint8_t)C;
+            hd[6] = (uint8_t)first_chunk_bytes;
+            hd[7] = (uint8_t)(first_chunk_bytes >> 8);
+            hd[8] = (uint8_t)N;
+            hd[9] = (uint8_t)(N >> 8);
+            for (int i = 0; i < 4; i++) hd[10 + i] = (uint8_t)(p.sample_rate >> (8 * i));
+            for (int i = 0; i < 4; i++) hd[14 + i] = (uint8_t)(st.n_frames >> (8 * i));
+            for (int i = 0; i < 4; i++) hd[18 + i] = 0;
+        }
+        out_lens[sidx] = written;
+        chunk0[sidx] = first_chunk_bytes;
+    }
+    if (state) {
+        for (uint32_t c = tid; c < C; c += T) {
+            int32_t *sp = state + ((uint64_t)sidx * C + c) * kEncStateWords;
+            for (int i = 0; i < 4; i++) {
+                sp[i] = st_h[c * 4 + i];
+                sp[4 + i] = st_w[c * 4 + i];
+            }
+            sp[8] = st_prev[c];
+        }
+    }
+}
+
+cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const EncStream *d_streams, const EncParams &p,
+                                  DevTables tabs, int32_t *d_state, uint64_t *d_out_lens, uint32_t *d_chunk0,
+                                  unsigned long long *d_ties, EncWorkspace ws, int *d_err, cudaStream_t stream)
+{
+    if (p.n_streams == 0) return cudaSuccess;
+    const uint32_t nsf = 1u << p.s, lpc = nsf < 32u ? nsf : 32u, cpw = 32u / lpc;
+    uint32_t warps = (p.channels + cpw - 1u) / cpw;
+    if (warps > 8u) warps = 8u;
+    if (p.vbr && warps < 4u) warps = 4u;  // the sort and the section writers are CTA-wide
+    const uint32_t T = warps * 32u;
+    const size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + 2u * (size_t)p.F * T + 16u;
+    if (smem > 200u * 1024u) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(encode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_generic_kernel<<<p.n_streams, T, smem, stream>>>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties,
+                                                          ws, d_err);
+    return cudaGetLastError();
+}
+
+}  // namespace sea

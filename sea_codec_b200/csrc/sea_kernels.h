@@ -1,0 +1,84 @@
+// sea_kernels.h -- launch interface between the C-ABI layer (capi.cu) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sea_common.cuh"
+
+namespace sea {
+
+// Device-side error codes written to the error word by kernels (first failure wins).
+enum : int { kDevOk = 0, kDevInvalidFrame = 1, kDevDomain = 2, kDevFallback = 3 /* staged kernel: use the generic path */ };
+
+// ---- decode ------------------------------------------------------------------------------------------------
+// One entry per stream; chains (chunk, channel) of all streams are numbered consecutively.
+struct DecStream {
+    uint64_t data_off;      // byte offset of the first chunk inside the batch buffer
+    uint64_t data_len;      // bytes available from data_off
+    uint64_t pcm_off;       // sample offset of the stream's PCM inside the output buffer
+    uint32_t total_frames;  // frames to produce (resolved by the host, decoder.rs:33-44)
+    uint32_t n_chunks;
+    uint32_t chain_begin;   // global id of the stream's first chain
+    uint16_t chunk_size;
+    uint16_t frames_per_chunk;
+    uint32_t channels;
+    uint32_t pad;
+};
+
+// Generic path: any per-chunk (type, sf bits, residual size, sf frames), any channel count, any alignment.
+cudaError_t launch_decode_generic(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, uint32_t n_streams,
+                                  uint64_t total_chains, DevTables tabs, int *d_err, cudaStream_t stream);
+
+// Fast path: uniform batch (every chunk CBR with the same header word, channels C in {1,2}); falls back is the
+// caller's job when *d_err reports a chunk whose header differs.
+struct DecFastParams {
+    uint32_t channels, N, chunk_size, F, s, b;
+    uint32_t hdr_word;       // expected little-endian first 4 bytes of every chunk
+    uint32_t n_streams;
+    uint64_t total_chunks;
+};
+bool decode_fast_supported(const DecFastParams &p);
+cudaError_t launch_decode_fast(const uint8_t *d_sea, uint64_t sea_len, int16_t *d_pcm, const DecStream *d_streams,
+                               const DecFastParams &p, DevTables tabs, int *d_err, cudaStream_t stream);
+
+// ---- encode ------------------------------------------------------------------------------------------------
+struct EncStream {
+    uint64_t pcm_off;   // sample offset of the stream's PCM
+    uint64_t out_off;   // byte offset of the stream's .sea (or of the raw chunk in chunk mode)
+    uint32_t n_frames;
+    uint32_t last_counts[3];  // VBR bucket counts [base-1, base+1, base+2] of the partial last chunk
+};
+
+struct EncParams {
+    uint32_t channels, N, F, s;
+    uint32_t hdr_bits;         // chunk header residual size
+    uint32_t vbr;              // 0/1
+    uint32_t base;             // VBR base size
+    uint32_t full_counts[3];   // VBR bucket counts [base-1, base+1, base+2] of a full chunk
+    uint32_t full_chunk_bytes;
+    uint32_t max_chunk_bytes;
+    uint32_t sample_rate;
+    uint32_t raw_chunk_mode;   // 1: write only the chunk at out_off, no file header (make_chunk seam)
+    uint32_t n_streams;
+};
+
+// Persistent per-channel encoder state (EncoderBase.lms + prev_scalefactor, encoder_base.rs:15-19): 9 int32 per channel
+constexpr int kEncStateWords = 9;
+
+struct EncWorkspace {
+    // per-stream VBR scratch (device), sized by enc_vbr_scratch_bytes()
+    uint8_t *vbr_scratch;
+    uint64_t vbr_scratch_stride;
+};
+uint64_t enc_vbr_scratch_bytes(const EncParams &p);
+
+// d_state: nullable; when set, n_streams * channels * 9 int32 loaded at start and stored at the end.
+// d_out_lens: per stream total bytes written; d_chunk0: per stream size of its first chunk; d_ties: VBR boundary ties.
+cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const EncStream *d_streams, const EncParams &p,
+                                  DevTables tabs, int32_t *d_state, uint64_t *d_out_lens, uint32_t *d_chunk0,
+                                  unsigned long long *d_ties, EncWorkspace ws, int *d_err, cudaStream_t stream);
+
+// ---- measurement -------------------------------------------------------------------------------------------
+cudaError_t launch_int32_peak(int mode, uint32_t *d_sink, uint64_t *lane_ops, cudaStream_t stream);
+
+}  // namespace sea
