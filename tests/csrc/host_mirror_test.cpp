@@ -1,0 +1,62 @@
+// Drives the C++ host mirror (include/sea_b200.hpp) the way tests/streaming.rs and examples/bench.rs drive the crate:
+//   host_mirror_test <pcm.raw> <channels> <rate> <bits> <vbr 0|1> <out_oneshot.sea> <out_stream.sea> <out_dec.raw>
+// one-shot sea_encode, chunk-at-a-time SeaEncoder, SeaDecoder over the result.  The pytest side compares the three
+// outputs with the oracle.  Needs a GPU (no CPU fallback).
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iterator>
+
+#include "../../include/sea_b200.hpp"
+
+static std::vector<uint8_t> slurp(const char *path)
+{
+    std::ifstream f(path, std::ios::binary);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+static void dump(const char *path, const void *p, size_t n)
+{
+    std::ofstream f(path, std::ios::binary);
+    f.write(static_cast<const char *>(p), (std::streamsize)n);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 9) return 2;
+    try {
+        std::vector<uint8_t> raw = slurp(argv[1]);
+        const uint32_t channels = (uint32_t)atoi(argv[2]), rate = (uint32_t)atoi(argv[3]);
+        sea::EncoderSettings st;
+        st.residual_bits = (float)atof(argv[4]);
+        st.vbr = atoi(argv[5]) != 0;
+        sea::Context ctx(0);
+        const int16_t *pcm = reinterpret_cast<const int16_t *>(raw.data());
+        const size_t n = raw.size() / 2;
+        std::vector<uint8_t> one = sea::sea_encode(ctx, pcm, n, rate, channels, st);
+        dump(argv[6], one.data(), one.size());
+
+        sea::SliceReader rd(raw.data(), raw.size());
+        sea::VecWriter wr;
+        sea::SeaEncoder<sea::SliceReader, sea::VecWriter> enc(ctx, (uint8_t)channels, rate, (uint32_t)(n / channels), st, rd, wr);
+        while (enc.encode_frame()) {}
+        enc.finalize();
+        dump(argv[7], wr.data.data(), wr.data.size());
+
+        sea::SliceReader rd2(wr.data.data(), wr.data.size());
+        sea::VecWriter pcm_out;
+        sea::SeaDecoder<sea::SliceReader, sea::VecWriter> dec(ctx, rd2, pcm_out);
+        while (dec.decode_frame()) {}
+        dec.finalize();
+        dump(argv[8], pcm_out.data.data(), pcm_out.data.size());
+        sea::SeaDecodeInfo info = sea::sea_decode(ctx, one.data(), one.size());
+        if (info.samples.size() * 2 != pcm_out.data.size() || memcmp(info.samples.data(), pcm_out.data.data(), pcm_out.data.size()) != 0) {
+            fprintf(stderr, "one-shot decode differs from streaming decode\n");
+            return 1;
+        }
+        printf("ok %zu %zu %zu\n", one.size(), wr.data.size(), pcm_out.data.size());
+        return 0;
+    } catch (const sea::SeaError &e) {
+        fprintf(stderr, "SeaError %d: %s\n", e.code, e.what());
+        return 3;
+    }
+}

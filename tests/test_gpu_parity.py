@@ -78,7 +78,17 @@ def test_decode_other_geometry(ctx, oracle, sfb, sff, fpc):
         pcm = gen_test_signal(channels, fpc * 3 + sff + 3, seed=sfb)
         st = oracle.make_settings(bits, vbr, sfb, sff, fpc)
         enc = oracle.sea_encode(pcm, 44100, channels, st)
-        assert np.array_equal(ctx.sea_decode(enc).samples, oracle.sea_decode(enc).samples)
+        try:
+            ref = oracle.sea_decode(enc).samples
+        except oracle.OracleError as e:
+            # e.g. N=200, F=5 VBR: base = floor(bits) - 2, the 2-bit size code wraps (chunk.rs:248 masks in release builds) and
+            # the reference cannot decode its own file; the GPU path must refuse the same input instead of inventing PCM
+            assert e.code == oracle.ERR_PANIC
+            with pytest.raises(S.SeaError) as ge:
+                ctx.sea_decode(enc)
+            assert ge.value.code == api.ERR_DOMAIN
+            continue
+        assert np.array_equal(ctx.sea_decode(enc).samples, ref)
 
 
 def test_decode_ragged_lengths(ctx, oracle):
@@ -185,6 +195,8 @@ def test_encode_multichannel_and_geometry(ctx, oracle):
         (1, dict(residual_bits=5.0, scale_factor_bits=6, scale_factor_frames=32, frames_per_chunk=320)),
         (4, dict(residual_bits=6.0, scale_factor_bits=2)),
         (17, dict(residual_bits=3.0)),
+        (1, dict(residual_bits=3.0, vbr=True, scale_factor_frames=5, frames_per_chunk=200)),  # wrapped VBR size codes
+        (2, dict(residual_bits=4.0, vbr=True, scale_factor_frames=5, frames_per_chunk=200)),
     ]
     for channels, kw in cases:
         n = kw.get("frames_per_chunk", 5120)
