@@ -169,9 +169,6 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
 {
     const uint32_t n_streams = (uint32_t)job.streams.size();
     if (job.total_chains == 0) return SEA_B200_OK;
-    CU(ctx->streams.reserve(sizeof(DecStream) * n_streams));
-    CU(cudaMemcpyAsync(ctx->streams.p, job.streams.data(), sizeof(DecStream) * n_streams, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
 
     DecFastParams fp = {};
     bool fast = false;
@@ -188,11 +185,57 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
         const uint32_t type = hdr_word & 255u;
         fast = (type == 1u || type == 2u) && (hdr_word >> 24) == 0x5Au && decode_fast_supported(fp);
     }
+    // Descriptor table on the device: [0, n) every chunk of every stream; when the unrolled kernel applies, [n, 2n) the full
+    // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
+    std::vector<DecStream> table(job.streams);
+    bool unrolled = fast && decode_unrolled_supported(fp) && (reinterpret_cast<uint64_t>(d_pcm) & 15u) == 0;
+    uint64_t chains_a = 0, chains_b = 0;
+    if (unrolled) {
+        table.resize((size_t)3 * n_streams);
+        for (uint32_t i = 0; i < n_streams && unrolled; i++) {
+            const DecStream &d = job.streams[i];
+            if (d.pcm_off % 8) unrolled = false;  // TMA stores need 16-byte aligned rows
+            uint64_t n_full = std::min<uint64_t>(d.total_frames / fp.N, d.n_chunks);
+            while (n_full > 0 && d.data_off + n_full * fp.chunk_size + 128 > sea_len) n_full--;
+            DecStream a = d, b = d;
+            a.n_chunks = (uint32_t)n_full;
+            a.total_frames = (uint32_t)(n_full * fp.N);
+            a.chain_begin = (uint32_t)chains_a;
+            chains_a += n_full * fp.channels;
+            b.data_off += n_full * fp.chunk_size;
+            b.data_len -= n_full * fp.chunk_size;
+            b.pcm_off += n_full * fp.N * fp.channels;
+            b.total_frames -= (uint32_t)(n_full * fp.N);
+            b.n_chunks -= (uint32_t)n_full;
+            b.chain_begin = (uint32_t)chains_b;
+            chains_b += (uint64_t)b.n_chunks * fp.channels;
+            table[(size_t)n_streams + i] = a;
+            table[(size_t)2 * n_streams + i] = b;
+        }
+        if (chains_a == 0) unrolled = false;
+    }
+    CU(ctx->streams.reserve(sizeof(DecStream) * table.size()));
+    CU(cudaMemcpyAsync(ctx->streams.p, table.data(), sizeof(DecStream) * table.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    const DecStream *d_all = ctx->streams.as<DecStream>();
+
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int dev_err = 0;
     if (fast) {
-        CU(launch_decode_fast(d_sea, sea_len, d_pcm, ctx->streams.as<DecStream>(), fp, ctx->tabs, ctx->d_err, ctx->stream));
-        ctx->launches++;
+        if (unrolled) {
+            DecFastParams fa = fp, fb = fp;
+            fa.total_chunks = chains_a / fp.channels;
+            fb.total_chunks = chains_b / fp.channels;
+            CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, ctx->d_err, ctx->stream));
+            ctx->launches++;
+            if (fb.total_chunks) {
+                CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, ctx->d_err, ctx->stream));
+                ctx->launches++;
+            }
+        } else {
+            CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all, fp, ctx->tabs, ctx->d_err, ctx->stream));
+            ctx->launches++;
+        }
         CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (dev_err != kDevOk) {  // some chunk is not what the fast path was specialised for: redo everything generically
@@ -201,7 +244,7 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
         }
     }
     if (!fast) {
-        CU(launch_decode_generic(d_sea, d_pcm, ctx->streams.as<DecStream>(), n_streams, job.total_chains, ctx->tabs, ctx->d_err, ctx->stream));
+        CU(launch_decode_generic(d_sea, d_pcm, d_all, n_streams, job.total_chains, ctx->tabs, ctx->d_err, ctx->stream));
         ctx->launches++;
         CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }

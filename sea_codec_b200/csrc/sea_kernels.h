@@ -41,6 +41,12 @@ bool decode_fast_supported(const DecFastParams &p);
 cudaError_t launch_decode_fast(const uint8_t *d_sea, uint64_t sea_len, int16_t *d_pcm, const DecStream *d_streams,
                                const DecFastParams &p, DevTables tabs, int *d_err, cudaStream_t stream);
 
+// Throughput path (decode_fast.cu): CBR, 1 or 2 channels, scale_factor_frames = 20, FULL chunks only, PCM offsets
+// multiples of 8 samples, and >= 128 readable bytes after every chunk it is given (TMA rows over-read a little).
+bool decode_unrolled_supported(const DecFastParams &p);
+cudaError_t launch_decode_unrolled(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
+                                   DevTables tabs, int *d_err, cudaStream_t stream);
+
 // ---- encode ------------------------------------------------------------------------------------------------
 struct EncStream {
     uint64_t pcm_off;   // sample offset of the stream's PCM
