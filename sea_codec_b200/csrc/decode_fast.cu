@@ -4,8 +4,10 @@
 // Same work as decode_staged_kernel (chunk.rs:69-213 parse, bits.rs:34-50 unpack, codec/decoder.rs:20-50 reconstruct), laid
 // out for the B200 issue-rate bound (the chain recurrence costs ~18 integer instructions per sample; HBM needs 2.4 B/sample):
 //   * one chain (chunk, channel) per lane, a warp owns 32/C consecutive chunks, a CTA of 32 warps owns one SM;
-//   * packed residuals arrive by TMA bulk copies (cp.async.bulk global->shared, mbarrier completion), one per chunk row per
-//     round, double buffered one round ahead; PCM leaves by TMA bulk stores (shared->global) of whole interleaved row tiles;
+//   * packed residuals arrive by 16-byte cp.async (LDGSTS) issued by the lanes of each chunk row, double buffered one round
+//     ahead; PCM leaves as whole interleaved row tiles with 128-bit shared loads / global stores.  (Round 1 first used TMA bulk
+//     copies for both directions: 48 bulk ops per warp-round, each serialised through the uniform datapath by an
+//     elect/broadcast loop, cost ~6 extra ALU-pipe instructions per sample; see profiles/r01_decode_unrolled_tma_v2_*.)
 //   * a round is RF frames with RF*C*B a multiple of 32 bits, so every field position inside a round is a compile-time
 //     constant: a field costs one shift and one LOP3 that also forms the look-up address;
 //   * the dequant row table is replicated per bank in shared memory (lane l reads bank l) when it fits, so the one dependent
@@ -19,38 +21,12 @@ namespace {
 __device__ __forceinline__ void report_f(int *err, int code) { atomicCAS(err, 0, code); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ int32_t lds_s32(uint32_t addr)
 {
     int32_t v;
@@ -88,18 +64,22 @@ struct UCfg {
     static constexpr int kHalfBits = HF * C * B;
     static constexpr int kNW = ((kHalfBits + 8 + 31) >> 5) + 1;    // words one half can touch (channel shift + straddle)
     // row buffer: up to 12 bytes of 16-byte alignment slack, then every word the last half reads (realign + funnel over-read)
-    static constexpr int kInBytes = round_up16(12 + 4 * ((((kHalves - 1) * kHalfBits) >> 5) + kNW + 2));
+    // input tile: word-major [word][row] so that "word w of every row" is one conflict-free wavefront; the words come in by
+    // 4-byte cp.async from the 4-byte aligned start of the round (byte phase is undone by the PRMT that also swaps bytes)
+    static constexpr int kInWords = (((kHalves - 1) * kHalfBits) >> 5) + kNW + 2;
+    static constexpr int kInBytes = kInWords * 4;  // per row and buffer
+    // output tile rows are dense (pitch = row bytes: 40 or 20 words, so LDS/STS of 4 or 8 consecutive rows tile all 32 banks);
+    // the 4 rows that would share a bank group rotate the words inside each 16-byte granule by rho = (row / kOutPeriod) & 3
     static constexpr int kOutBytes = HF * C * 2;
-    static constexpr int kOutPitch = pitch16_odd(kOutBytes);
-    static constexpr int kWarpBytes = 16 + 2 * kRows * kInBytes + kRows * kOutPitch;
+    static constexpr int kOutPitch = kOutBytes;
+    static constexpr int kOutPeriod = C == 2 ? 4 : 8;
+    static constexpr int kWarpBytes = 2 * kRows * kInBytes + kRows * kOutPitch;
     // warps per CTA (one CTA per SM): as many as fit next to <= 37 KB of look-up table, a multiple of 4 (one per SMSP)
     static constexpr int kWarpsFit = (190 * 1024 / kWarpBytes) / 4 * 4;
     static constexpr int kWarps = kWarpsFit < 32 ? kWarpsFit : 32;
 };
 
 }  // namespace
-
-constexpr int kDevInternal = kDevDomain;  // an mbarrier that never completes is reported, never waited on forever
 
 template <int C, int B, bool REPL>
 __global__ void __launch_bounds__(UCfg<C, B>::kWarps * 32, 1)
@@ -130,10 +110,8 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint32_t lut_sh = smem_u32(lut) + (REPL ? lane * 4u : 0u);
 
     uint8_t *wbase = smem + warp * Cfg::kWarpBytes;
-    const uint32_t bar0 = smem_u32(wbase);  // two mbarriers, one per input buffer
-    const uint32_t in_sh = smem_u32(wbase + 16);
-    uint8_t *in_rows = wbase + 16;
-    uint8_t *out_rows = wbase + 16 + 2 * Cfg::kRows * Cfg::kInBytes;
+    uint8_t *in_rows = wbase;  // [2][kInWords][kRows] words
+    uint8_t *out_rows = wbase + 2 * Cfg::kRows * Cfg::kInBytes;
 
     const uint32_t j = lane / C, c = lane % C;
     uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + j;  // global chunk index
@@ -169,61 +147,77 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint32_t prmt_sel = 0x0123u + bp * 0x1111u;  // byte swap + byte realign in one PRMT
     const uint32_t cB = c * B;                         // my channel's bit offset inside a frame
 
-    if (lane == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
     const uint32_t n_rounds = p.N / Cfg::RF;
+    constexpr int kBlocks = Cfg::RF / Cfg::F;
+    constexpr int kOutGran = Cfg::kOutBytes / 16;
+    constexpr int kInPerLane = (Cfg::kInWords + C - 1) / C, kOutPerLane = (kOutGran + C - 1) / C;
+
+    // The C lanes of a row fetch its next slice word by word (4-byte cp.async, lane c takes words c, c+C, ...), one round ahead.
+    const uint32_t my_in_sh = smem_u32(in_rows) + (c * Cfg::kRows + j) * 4u;
     auto issue_round = [&](uint32_t r) {
-        const uint32_t buf = r & 1u;
-        if (lane == 0) mbar_expect_tx(bar0 + 8u * buf, Cfg::kRows * Cfg::kInBytes);
-        __syncwarp();
-        if (c == 0) {
-            const uint64_t a = (res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)15;
-            bulk_g2s(in_sh + (buf * Cfg::kRows + j) * Cfg::kInBytes, sea + a, Cfg::kInBytes, bar0 + 8u * buf);
+        const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)3) + c * 4u;
+        const uint32_t dst = my_in_sh + (r & 1u) * (Cfg::kRows * Cfg::kInBytes);
+#pragma unroll
+        for (int t = 0; t < kInPerLane; t++)
+            if (t * C + (int)c < Cfg::kInWords) cp_async4(dst + t * C * Cfg::kRows * 4, src + t * C * 4);
+        cp_async_commit();
+    };
+    // scale-factor bytes are prefetched one round ahead too (they come straight from global memory)
+    uint32_t sf_raw[kBlocks], sf_raw2[kBlocks];
+    auto fetch_sf = [&](uint32_t r, uint32_t *raw, uint32_t *raw2) {
+#pragma unroll
+        for (int q = 0; q < kBlocks; q++) {
+            raw2[q] = 0;
+            if (s == 4u && C == 2) {
+                raw[q] = __ldg(sfp + r * kBlocks + q);
+            } else if (s == 4u && C == 1) {
+                raw[q] = __ldg(sfp + ((r * kBlocks + q) >> 1));
+            } else {
+                const uint32_t bit = ((r * kBlocks + q) * C + c) * s;
+                raw[q] = __ldg(sfp + (bit >> 3));
+                if ((bit & 7u) + s > 8u) raw2[q] = __ldg(sfp + (bit >> 3) + 1);
+            }
         }
     };
     issue_round(0);
+    fetch_sf(0, sf_raw, sf_raw2);
 
-    const uint32_t out_sh = smem_u32(out_rows + j * Cfg::kOutPitch);
-    int16_t *my_out = reinterpret_cast<int16_t *>(out_rows + j * Cfg::kOutPitch) + c;
+    // my row of the output tile: logical word m of every granule lives at physical word (m + rho) & 3
+    const uint32_t rho = (j / Cfg::kOutPeriod) & 3u;
+    uint8_t *my_row = out_rows + j * Cfg::kOutPitch;
+    uint8_t *st_base[4];       // per logical word-in-granule: where my samples go (stereo: + 2c inside the word)
+    const uint32_t *ld_base[4];  // per logical word-in-granule: where the copy-out reads it (my first granule is granule c)
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int32_t rot = (int32_t)((m + rho) & 3u) - m;
+        st_base[m] = my_row + rot * 4 + (C == 2 ? 2 * c : 0);
+        ld_base[m] = reinterpret_cast<const uint32_t *>(my_row) + ((m + rho) & 3u) + c * 4u;
+    }
+    uint4 *my_dst = reinterpret_cast<uint4 *>(out) + c;
 
     for (uint32_t r = 0; r < n_rounds; r++) {
-        if (r + 1 < n_rounds) issue_round(r + 1);  // buffer (r+1)&1 was last read in round r-1; the __syncwarp inside orders it
-        {
-            uint32_t spins = 0;
-            while (!mbar_try_wait(bar0 + 8u * (r & 1u), (r >> 1) & 1u)) {
-                if (++spins > (1u << 24)) {
-                    report_f(err, kDevInternal);
-                    break;
-                }
-            }
-        }
-        const uint32_t bo = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & 15u;
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_rows + ((r & 1u) * Cfg::kRows + j) * Cfg::kInBytes) + (bo >> 2);
+        // all lanes are done with buffer (r+1)&1 (read in round r-1): refill it, then wait for this round's slice
+        __syncwarp();
+        if (r + 1 < n_rounds) issue_round(r + 1);
+        else cp_async_commit();
+        cp_async_wait1();
+        __syncwarp();
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_rows + (r & 1u) * (Cfg::kRows * Cfg::kInBytes)) + j;
 
-        // scale factors of this round's blocks
-        constexpr int kBlocks = Cfg::RF / Cfg::F;
+        // scale factors of this round's blocks (bytes fetched during the previous round), then prefetch the next round's
         uint32_t sfv[kBlocks];
-        if (s == 4u && C == 2) {
 #pragma unroll
-            for (int q = 0; q < kBlocks; q++) sfv[q] = ((uint32_t)__ldg(sfp + r * kBlocks + q) >> (4u * (1u - c))) & 15u;
-        } else if (s == 4u && C == 1) {
-#pragma unroll
-            for (int q = 0; q < kBlocks; q++) sfv[q] = ((uint32_t)__ldg(sfp + ((r * kBlocks + q) >> 1)) >> (4u * (1u - (q & 1)))) & 15u;
-        } else {
-#pragma unroll
-            for (int q = 0; q < kBlocks; q++) {
-                const uint64_t bit = (uint64_t)((r * kBlocks + q) * C + c) * s;
-                const uint32_t sh = (uint32_t)bit & 7u;
-                uint32_t v = (uint32_t)__ldg(sfp + (bit >> 3)) << 8;
-                if (sh + s > 8u) v |= (uint32_t)__ldg(sfp + (bit >> 3) + 1);
-                sfv[q] = (v >> (16u - sh - s)) & ((1u << s) - 1u);
+        for (int q = 0; q < kBlocks; q++) {
+            if (s == 4u && C == 2) {
+                sfv[q] = (sf_raw[q] >> (4u * (1u - c))) & 15u;
+            } else if (s == 4u && C == 1) {
+                sfv[q] = (sf_raw[q] >> (4u * (1u - (q & 1)))) & 15u;
+            } else {
+                const uint32_t sh = (((r * kBlocks + q) * C + c) * s) & 7u;
+                sfv[q] = (((sf_raw[q] << 8) | sf_raw2[q]) >> (16u - sh - s)) & ((1u << s) - 1u);
             }
         }
+        if (r + 1 < n_rounds) fetch_sf(r + 1, sf_raw, sf_raw2);
 
 #pragma unroll
         for (int hh = 0; hh < Cfg::kHalves; hh++) {
@@ -233,15 +227,14 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
             constexpr int kNW = Cfg::kNW;
             uint32_t V[kNW + 2], W[kNW + 1];
 #pragma unroll
-            for (int t = 0; t < kNW + 2; t++) V[t] = words[wlo + t];
+            for (int t = 0; t < kNW + 2; t++) V[t] = words[(wlo + t) * Cfg::kRows];
 #pragma unroll
             for (int t = 0; t < kNW + 1; t++) W[t] = __byte_perm(V[t], V[t + 1], prmt_sel);
             if (C == 2) {
 #pragma unroll
                 for (int t = 0; t < kNW; t++) W[t] = __funnelshift_l(W[t + 1], W[t], cB);
             }
-            bulk_wait_read0();  // the previous tile's bulk store has finished reading out_rows
-            __syncwarp();
+            __syncwarp();  // the previous tile has been copied out by every lane of the row
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const uint32_t sf = sfv[hh * 2 + q];
@@ -263,7 +256,10 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
                     const uint32_t acc = (uint32_t)w[0] * (uint32_t)h[0] + (uint32_t)w[1] * (uint32_t)h[1] + (uint32_t)w[2] * (uint32_t)h[2] +
                                          (uint32_t)w[3] * (uint32_t)h[3];
                     const int32_t y = clamp_i16((int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d));
-                    my_out[fi * C] = (int16_t)y;
+                    {
+                        const int lbyte = (fi * C) * 2;  // logical byte of (frame fi, channel 0); my channel adds 2c (in st_base)
+                        *reinterpret_cast<int16_t *>(st_base[(lbyte >> 2) & 3] + (lbyte >> 2) * 4 + (C == 1 ? (lbyte & 2) : 0)) = (int16_t)y;
+                    }
                     const int32_t delta = d >> 4;
                     w[0] += delta * sg[0];
                     w[1] += delta * sg[1];
@@ -273,15 +269,23 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
                     sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (y >> 31) | 1;
                 }
             }
-            fence_async_smem();  // make the generic-proxy writes of the tile visible to the bulk-copy engine
+            // copy-out: the C lanes of a row move its tile with 128-bit loads/stores (adjacent lanes, adjacent 16 bytes)
             __syncwarp();
-            if (c == 0 && valid) {
-                bulk_s2g(out + (uint64_t)(r * Cfg::RF + hh * Cfg::HF) * C, out_sh, Cfg::kOutBytes);
-                bulk_commit();
+            if (valid) {
+                uint4 *dst = my_dst + (size_t)(r * Cfg::RF + hh * Cfg::HF) * C * 2 / 16;
+#pragma unroll
+                for (int t = 0; t < kOutPerLane; t++)
+                    if (t * C + (int)c < kOutGran) {
+                        uint4 q;
+                        q.x = ld_base[0][t * C * 4];
+                        q.y = ld_base[1][t * C * 4];
+                        q.z = ld_base[2][t * C * 4];
+                        q.w = ld_base[3][t * C * 4];
+                        dst[t * C] = q;
+                    }
             }
         }
     }
-    bulk_wait0();
 }
 
 // Shared-memory plan of decode_unrolled_kernel<C, B> for scale_factor_bits s: replicated table when it is <= 16 KB.
