@@ -2,16 +2,21 @@
 // full chunks): decode_unrolled_kernel<C, B>.
 //
 // Same work as decode_staged_kernel (chunk.rs:69-213 parse, bits.rs:34-50 unpack, codec/decoder.rs:20-50 reconstruct), laid
-// out for the B200 issue-rate bound (the chain recurrence costs ~18 integer instructions per sample; HBM needs 2.4 B/sample):
-//   * one chain (chunk, channel) per lane, a warp owns 32/C consecutive chunks, a CTA of 32 warps owns one SM;
-//   * packed residuals arrive by 16-byte cp.async (LDGSTS) issued by the lanes of each chunk row, double buffered one round
-//     ahead; PCM leaves as whole interleaved row tiles with 128-bit shared loads / global stores.  (Round 1 first used TMA bulk
-//     copies for both directions: 48 bulk ops per warp-round, each serialised through the uniform datapath by an
-//     elect/broadcast loop, cost ~6 extra ALU-pipe instructions per sample; see profiles/r01_decode_unrolled_tma_v2_*.)
+// out for what bounds it on B200.  The chain recurrence costs ~18 integer instructions per sample while HBM needs only
+// 2.4 B/sample, so the limits are the issue slots, the ALU pipe and the shared-memory data pipe, in that order of discovery
+// (profiles/r01_decode_*):
+//   * one CHUNK per lane (all C channels of it: C independent recurrences per thread, fields of a frame are adjacent bits), a
+//     warp owns 32 consecutive chunks, one CTA per SM;
 //   * a round is RF frames with RF*C*B a multiple of 32 bits, so every field position inside a round is a compile-time
 //     constant: a field costs one shift and one LOP3 that also forms the look-up address;
-//   * the dequant row table is replicated per bank in shared memory (lane l reads bank l) when it fits, so the one dependent
-//     shared-memory load per sample is conflict free.
+//   * packed residuals are staged word-major ([word][chunk row]) by 4-byte cp.async one round ahead, so "word w of every row"
+//     is one conflict-free shared-memory wavefront; the byte phase of the unaligned section is undone by the same PRMT that
+//     swaps to big-endian;
+//   * the dequant row table is replicated per bank (lane l reads bank l) when it fits: the one dependent shared load per
+//     sample is conflict free;
+//   * PCM goes straight from registers to global memory, 16 bytes (4 stereo frames / 8 mono frames) per lane per store: the
+//     output never touches shared memory.  (Earlier variants staged it: TMA bulk stores cost ~6 ALU instructions per sample in
+//     elect/broadcast loops, an STS.U16 + LDS/STG tile copy saturated the shared-memory pipe at 85 %.)
 #include "sea_kernels.h"
 
 namespace sea {
@@ -19,7 +24,6 @@ namespace sea {
 namespace {
 
 __device__ __forceinline__ void report_f(int *err, int code) { atomicCAS(err, 0, code); }
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
 {
@@ -45,38 +49,23 @@ __device__ __forceinline__ uint32_t find_stream_f(const DecStream *streams, uint
     return lo;
 }
 
-constexpr int round_up16(int v) { return (v + 15) / 16 * 16; }
-constexpr int pitch16_odd(int bytes)  // multiple of 16 with an odd number of 16-byte units: rows spread over all bank groups
-{
-    int p = round_up16(bytes);
-    return ((p / 16) % 2) ? p : p + 16;
-}
-
 template <int C, int B>
 struct UCfg {
-    static constexpr int F = 20;                                   // scale_factor_frames this kernel is unrolled for
-    static constexpr int kRows = 32 / C;                           // chunks per warp
-    static constexpr int RF = ((C * B) % 2 == 0) ? 80 : 160;       // frames per round: RF*C*B % 32 == 0 and RF % F == 0
+    static constexpr int F = 20;                              // scale_factor_frames this kernel is unrolled for
+    static constexpr int kRows = 32;                          // chunks per warp: one per lane
+    static constexpr int RF = ((C * B) % 2 == 0) ? 80 : 160;  // frames per round: RF*C*B % 32 == 0 and RF % F == 0
     static constexpr int kRoundBits = RF * C * B;
     static constexpr int kRoundBytes = kRoundBits / 8;
-    static constexpr int HF = 40;                                  // frames per output tile (two blocks)
+    static constexpr int HF = 40;                             // frames per window refill (two blocks)
     static constexpr int kHalves = RF / HF;
     static constexpr int kHalfBits = HF * C * B;
-    static constexpr int kNW = ((kHalfBits + 8 + 31) >> 5) + 1;    // words one half can touch (channel shift + straddle)
-    // row buffer: up to 12 bytes of 16-byte alignment slack, then every word the last half reads (realign + funnel over-read)
-    // input tile: word-major [word][row] so that "word w of every row" is one conflict-free wavefront; the words come in by
-    // 4-byte cp.async from the 4-byte aligned start of the round (byte phase is undone by the PRMT that also swaps bytes)
-    static constexpr int kInWords = (((kHalves - 1) * kHalfBits) >> 5) + kNW + 2;
-    static constexpr int kInBytes = kInWords * 4;  // per row and buffer
-    // output tile rows are dense (pitch = row bytes: 40 or 20 words, so LDS/STS of 4 or 8 consecutive rows tile all 32 banks);
-    // the 4 rows that would share a bank group rotate the words inside each 16-byte granule by rho = (row / kOutPeriod) & 3
-    static constexpr int kOutBytes = HF * C * 2;
-    static constexpr int kOutPitch = kOutBytes;
-    static constexpr int kOutPeriod = C == 2 ? 4 : 8;
-    static constexpr int kWarpBytes = 2 * kRows * kInBytes + kRows * kOutPitch;
-    // warps per CTA (one CTA per SM): as many as fit next to <= 37 KB of look-up table, a multiple of 4 (one per SMSP)
+    static constexpr int kNW = ((kHalfBits + 31 + 31) >> 5);  // big-endian words one half can touch (start offset <= 31 bits)
+    static constexpr int kInWords = (((kHalves - 1) * kHalfBits) >> 5) + kNW + 1;  // + one raw word for the byte realign
+    static constexpr int kWarpBytes = 2 * kInWords * kRows * 4;                    // double buffered [word][row]
+    static constexpr int kOutFrames = 8 / C;                  // frames per 16-byte store
+    // warps per CTA (one CTA per SM): as many as fit next to <= 33 KB of table, registers allowing (<= 24), multiple of 4
     static constexpr int kWarpsFit = (190 * 1024 / kWarpBytes) / 4 * 4;
-    static constexpr int kWarps = kWarpsFit < 32 ? kWarpsFit : 32;
+    static constexpr int kWarps = kWarpsFit < 24 ? kWarpsFit : 24;
 };
 
 }  // namespace
@@ -91,9 +80,9 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint32_t s = p.s;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
-    // ---- dequant rows of residual size B: lut[sf][code], replicated per bank when REPL (entry stride 128 B, lane l at +4l)
+    // ---- dequant rows of residual size B: lut[sf][code], replicated per bank when REPL (entry stride 128 B, lane l at +4l).
+    // The table sits after the warp tiles at an address aligned to its own size, so "row base | code offset" never carries.
     constexpr int kShift = REPL ? 7 : 2;  // log2 of the byte stride between consecutive codes
-    // the table sits after the warp tiles at an address aligned to its own size, so "row base | code offset" never carries
     const uint32_t smem_sh = smem_u32(smem);
     const uint32_t lut_abs = (smem_sh + Cfg::kWarps * Cfg::kWarpBytes + lut_align - 1u) & ~(lut_align - 1u);
     int32_t *lut = reinterpret_cast<int32_t *>(smem + (lut_abs - smem_sh));
@@ -107,16 +96,13 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
         }
     }
     __syncthreads();
-    const uint32_t lut_sh = smem_u32(lut) + (REPL ? lane * 4u : 0u);
+    const uint32_t lut_sh = lut_abs + (REPL ? lane * 4u : 0u);
 
-    uint8_t *wbase = smem + warp * Cfg::kWarpBytes;
-    uint8_t *in_rows = wbase;  // [2][kInWords][kRows] words
-    uint8_t *out_rows = wbase + 2 * Cfg::kRows * Cfg::kInBytes;
+    uint8_t *in_words = smem + warp * Cfg::kWarpBytes;  // [2][kInWords][32 rows]
 
-    const uint32_t j = lane / C, c = lane % C;
-    uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + j;  // global chunk index
+    uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + lane;  // global chunk index
     const bool valid = g < p.total_chunks;
-    if (!valid) g = p.total_chunks - 1;  // idle rows shadow the last chunk and never store
+    if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
 
     const DecStream st = streams[find_stream_f(streams, p.n_streams, g * C)];
     const uint32_t k = (uint32_t)(g - st.chain_begin / C);
@@ -126,163 +112,128 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
         const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
         if (word != p.hdr_word) report_f(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
     }
-    int32_t w[4], h[4], sg[4];
-    {
+    int32_t w[C][4], h[C][4], sg[C][4];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
         const uint8_t *l = ck + 4u + 16u * c;  // lms.rs:80-94
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            h[i] = (int16_t)(l[2 * i] | (l[2 * i + 1] << 8));
-            w[i] = (int16_t)(l[8 + 2 * i] | (l[8 + 2 * i + 1] << 8));
-            sg[i] = (h[i] >> 31) | 1;
+            h[c][i] = (int16_t)(l[2 * i] | (l[2 * i + 1] << 8));
+            w[c][i] = (int16_t)(l[8 + 2 * i] | (l[8 + 2 * i + 1] << 8));
+            sg[c][i] = (h[c][i] >> 31) | 1;
         }
     }
     const uint32_t items = (p.N / Cfg::F) * C;
     const uint64_t sf_off = ck_off + 4u + 16u * C;
     const uint64_t res_off = sf_off + div_ceil_u32(items * s, 8u);
     const uint8_t *sfp = sea + sf_off;
-    int16_t *out = pcm + st.pcm_off + (uint64_t)k * p.N * C;
+    uint4 *out = reinterpret_cast<uint4 *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
 
-    // byte phase of the residual section inside its 16-byte granule: constant over rounds modulo 4 (kRoundBytes % 4 == 0)
-    const uint32_t bp = (uint32_t)res_off & 3u;
-    const uint32_t prmt_sel = 0x0123u + bp * 0x1111u;  // byte swap + byte realign in one PRMT
-    const uint32_t cB = c * B;                         // my channel's bit offset inside a frame
+    // byte phase of the residual section inside a 32-bit word: the same in every round (kRoundBytes % 4 == 0)
+    const uint32_t prmt_sel = 0x0123u + ((uint32_t)res_off & 3u) * 0x1111u;  // byte swap + byte realign in one PRMT
 
     const uint32_t n_rounds = p.N / Cfg::RF;
     constexpr int kBlocks = Cfg::RF / Cfg::F;
-    constexpr int kOutGran = Cfg::kOutBytes / 16;
-    constexpr int kInPerLane = (Cfg::kInWords + C - 1) / C, kOutPerLane = (kOutGran + C - 1) / C;
 
-    // The C lanes of a row fetch its next slice word by word (4-byte cp.async, lane c takes words c, c+C, ...), one round ahead.
-    const uint32_t my_in_sh = smem_u32(in_rows) + (c * Cfg::kRows + j) * 4u;
+    // Each lane fetches its own row's next slice word by word into the word-major tile, one round ahead.
+    const uint32_t my_in_sh = smem_u32(in_words) + lane * 4u;
     auto issue_round = [&](uint32_t r) {
-        const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)3) + c * 4u;
-        const uint32_t dst = my_in_sh + (r & 1u) * (Cfg::kRows * Cfg::kInBytes);
+        const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)3);
+        const uint32_t dst = my_in_sh + (r & 1u) * (Cfg::kInWords * Cfg::kRows * 4);
 #pragma unroll
-        for (int t = 0; t < kInPerLane; t++)
-            if (t * C + (int)c < Cfg::kInWords) cp_async4(dst + t * C * Cfg::kRows * 4, src + t * C * 4);
+        for (int t = 0; t < Cfg::kInWords; t++) cp_async4(dst + t * Cfg::kRows * 4, src + t * 4);
         cp_async_commit();
     };
-    // scale-factor bytes are prefetched one round ahead too (they come straight from global memory)
-    uint32_t sf_raw[kBlocks], sf_raw2[kBlocks];
-    auto fetch_sf = [&](uint32_t r, uint32_t *raw, uint32_t *raw2) {
+    // scale-factor bytes are prefetched one round ahead too (they come straight from global memory): one byte pair per field
+    constexpr int kSfFields = kBlocks * C;
+    uint32_t sf_raw[kSfFields];
+    auto fetch_sf = [&](uint32_t r) {
 #pragma unroll
-        for (int q = 0; q < kBlocks; q++) {
-            raw2[q] = 0;
-            if (s == 4u && C == 2) {
-                raw[q] = __ldg(sfp + r * kBlocks + q);
-            } else if (s == 4u && C == 1) {
-                raw[q] = __ldg(sfp + ((r * kBlocks + q) >> 1));
+        for (int q = 0; q < kSfFields; q++) {
+            const uint32_t bit = (r * kSfFields + q) * s;
+            if (s == 4u) {
+                sf_raw[q] = __ldg(sfp + (bit >> 3));  // fields never straddle a byte
             } else {
-                const uint32_t bit = ((r * kBlocks + q) * C + c) * s;
-                raw[q] = __ldg(sfp + (bit >> 3));
-                if ((bit & 7u) + s > 8u) raw2[q] = __ldg(sfp + (bit >> 3) + 1);
+                sf_raw[q] = ((uint32_t)__ldg(sfp + (bit >> 3)) << 8) | ((bit & 7u) + s > 8u ? (uint32_t)__ldg(sfp + (bit >> 3) + 1) : 0u);
             }
         }
     };
     issue_round(0);
-    fetch_sf(0, sf_raw, sf_raw2);
-
-    // my row of the output tile: logical word m of every granule lives at physical word (m + rho) & 3
-    const uint32_t rho = (j / Cfg::kOutPeriod) & 3u;
-    uint8_t *my_row = out_rows + j * Cfg::kOutPitch;
-    uint8_t *st_base[4];       // per logical word-in-granule: where my samples go (stereo: + 2c inside the word)
-    const uint32_t *ld_base[4];  // per logical word-in-granule: where the copy-out reads it (my first granule is granule c)
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const int32_t rot = (int32_t)((m + rho) & 3u) - m;
-        st_base[m] = my_row + rot * 4 + (C == 2 ? 2 * c : 0);
-        ld_base[m] = reinterpret_cast<const uint32_t *>(my_row) + ((m + rho) & 3u) + c * 4u;
-    }
-    uint4 *my_dst = reinterpret_cast<uint4 *>(out) + c;
+    fetch_sf(0);
 
     for (uint32_t r = 0; r < n_rounds; r++) {
-        // all lanes are done with buffer (r+1)&1 (read in round r-1): refill it, then wait for this round's slice
-        __syncwarp();
+        // my buffer (r+1)&1 was consumed in round r-1 (only I read my row): refill it, then wait for this round's slice
         if (r + 1 < n_rounds) issue_round(r + 1);
         else cp_async_commit();
         cp_async_wait1();
-        __syncwarp();
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_rows + (r & 1u) * (Cfg::kRows * Cfg::kInBytes)) + j;
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_words + (r & 1u) * (Cfg::kInWords * Cfg::kRows * 4)) + lane;
 
         // scale factors of this round's blocks (bytes fetched during the previous round), then prefetch the next round's
-        uint32_t sfv[kBlocks];
+        uint32_t sfv[kSfFields];
 #pragma unroll
-        for (int q = 0; q < kBlocks; q++) {
-            if (s == 4u && C == 2) {
-                sfv[q] = (sf_raw[q] >> (4u * (1u - c))) & 15u;
-            } else if (s == 4u && C == 1) {
-                sfv[q] = (sf_raw[q] >> (4u * (1u - (q & 1)))) & 15u;
-            } else {
-                const uint32_t sh = (((r * kBlocks + q) * C + c) * s) & 7u;
-                sfv[q] = (((sf_raw[q] << 8) | sf_raw2[q]) >> (16u - sh - s)) & ((1u << s) - 1u);
-            }
+        for (int q = 0; q < kSfFields; q++) {
+            const uint32_t sh = ((r * kSfFields + q) * s) & 7u;
+            if (s == 4u) sfv[q] = (sf_raw[q] >> (4u - sh)) & 15u;
+            else sfv[q] = (sf_raw[q] >> (16u - sh - s)) & ((1u << s) - 1u);
         }
-        if (r + 1 < n_rounds) fetch_sf(r + 1, sf_raw, sf_raw2);
+        if (r + 1 < n_rounds) fetch_sf(r + 1);
 
 #pragma unroll
         for (int hh = 0; hh < Cfg::kHalves; hh++) {
-            // window of this half: big-endian words, realigned so that my field i sits at bit i*C*B of W[0..]
+            // window of this half: big-endian words W[0..], frame fi / channel c sits at bit (hh*kHB - 32*wlo) + (fi*C + c)*B
             constexpr int kHB = Cfg::kHalfBits;
             const int wlo = (hh * kHB) >> 5;
             constexpr int kNW = Cfg::kNW;
-            uint32_t V[kNW + 2], W[kNW + 1];
+            uint32_t V[kNW + 1], W[kNW];
 #pragma unroll
-            for (int t = 0; t < kNW + 2; t++) V[t] = words[(wlo + t) * Cfg::kRows];
+            for (int t = 0; t < kNW + 1; t++) V[t] = words[(wlo + t) * Cfg::kRows];
 #pragma unroll
-            for (int t = 0; t < kNW + 1; t++) W[t] = __byte_perm(V[t], V[t + 1], prmt_sel);
-            if (C == 2) {
-#pragma unroll
-                for (int t = 0; t < kNW; t++) W[t] = __funnelshift_l(W[t + 1], W[t], cB);
-            }
-            __syncwarp();  // the previous tile has been copied out by every lane of the row
+            for (int t = 0; t < kNW; t++) W[t] = __byte_perm(V[t], V[t + 1], prmt_sel);
+
+            uint32_t ow[4];  // 16 bytes of interleaved PCM being assembled
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                const uint32_t sf = sfv[hh * 2 + q];
-                const uint32_t rowbase = lut_sh + (sf << (B + kShift));
+                uint32_t rowbase[C];
+#pragma unroll
+                for (int c = 0; c < C; c++) rowbase[c] = lut_sh + (sfv[(hh * 2 + q) * C + c] << (B + kShift));
 #pragma unroll
                 for (int i = 0; i < Cfg::F; i++) {
-                    const int fi = q * Cfg::F + i;                      // frame inside the half
-                    const int bit = (hh * kHB) - (wlo << 5) + fi * C * B;  // compile-time position of my field in W[]
-                    const int wd = bit >> 5, off = bit & 31;
-                    uint32_t x;
-                    if (off + B <= 32) {
-                        const int rs = 32 - off - B - kShift;
-                        x = rs >= 0 ? (W[wd] >> (rs & 31)) : (W[wd] << ((-rs) & 31));
-                    } else {
-                        x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - B - kShift) & 31);
-                    }
-                    const uint32_t addr = (x & (((1u << B) - 1u) << kShift)) | rowbase;
-                    const int32_t d = lds_s32(addr);
-                    const uint32_t acc = (uint32_t)w[0] * (uint32_t)h[0] + (uint32_t)w[1] * (uint32_t)h[1] + (uint32_t)w[2] * (uint32_t)h[2] +
-                                         (uint32_t)w[3] * (uint32_t)h[3];
-                    const int32_t y = clamp_i16((int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d));
-                    {
-                        const int lbyte = (fi * C) * 2;  // logical byte of (frame fi, channel 0); my channel adds 2c (in st_base)
-                        *reinterpret_cast<int16_t *>(st_base[(lbyte >> 2) & 3] + (lbyte >> 2) * 4 + (C == 1 ? (lbyte & 2) : 0)) = (int16_t)y;
-                    }
-                    const int32_t delta = d >> 4;
-                    w[0] += delta * sg[0];
-                    w[1] += delta * sg[1];
-                    w[2] += delta * sg[2];
-                    w[3] += delta * sg[3];
-                    h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = y;
-                    sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (y >> 31) | 1;
-                }
-            }
-            // copy-out: the C lanes of a row move its tile with 128-bit loads/stores (adjacent lanes, adjacent 16 bytes)
-            __syncwarp();
-            if (valid) {
-                uint4 *dst = my_dst + (size_t)(r * Cfg::RF + hh * Cfg::HF) * C * 2 / 16;
+                    const int fi = q * Cfg::F + i;  // frame inside the half
+                    int32_t y[C];
 #pragma unroll
-                for (int t = 0; t < kOutPerLane; t++)
-                    if (t * C + (int)c < kOutGran) {
-                        uint4 q;
-                        q.x = ld_base[0][t * C * 4];
-                        q.y = ld_base[1][t * C * 4];
-                        q.z = ld_base[2][t * C * 4];
-                        q.w = ld_base[3][t * C * 4];
-                        dst[t * C] = q;
+                    for (int c = 0; c < C; c++) {
+                        const int bit = (hh * kHB) - (wlo << 5) + (fi * C + c) * B;  // compile-time position of the field in W[]
+                        const int wd = bit >> 5, off = bit & 31;
+                        uint32_t x;
+                        if (off + B <= 32) {
+                            const int rs = 32 - off - B - kShift;
+                            x = rs >= 0 ? (W[wd] >> (rs & 31)) : (W[wd] << ((-rs) & 31));
+                        } else {
+                            x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - B - kShift) & 31);
+                        }
+                        const int32_t d = lds_s32((x & (((1u << B) - 1u) << kShift)) | rowbase[c]);
+                        const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
+                                             (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
+                        y[c] = clamp_i16((int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d));
+                        const int32_t delta = d >> 4;
+                        w[c][0] += delta * sg[c][0];
+                        w[c][1] += delta * sg[c][1];
+                        w[c][2] += delta * sg[c][2];
+                        w[c][3] += delta * sg[c][3];
+                        h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
+                        sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = (y[c] >> 31) | 1;
                     }
+                    // interleaved i16 PCM: 4 stereo frames or 8 mono frames fill one 16-byte store
+                    const int fa = hh * Cfg::HF + fi;  // frame inside the round
+                    if (C == 2) {
+                        ow[fa & 3] = __byte_perm((uint32_t)y[0], (uint32_t)y[C - 1], 0x5410);
+                    } else {
+                        if ((fa & 1) == 0) ow[(fa >> 1) & 3] = (uint32_t)y[0] & 0xffffu;
+                        else ow[(fa >> 1) & 3] = __byte_perm(ow[(fa >> 1) & 3], (uint32_t)y[0], 0x5410);
+                    }
+                    if ((fa % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid)
+                        out[(size_t)r * (Cfg::RF / Cfg::kOutFrames) + fa / Cfg::kOutFrames] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
             }
         }
     }
