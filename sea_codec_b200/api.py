@@ -297,7 +297,7 @@ class Context:
         ptotal = 0
         for i in range(len(files)):
             pcm_off[i] = ptotal
-            ptotal += (int(caps[i]) + 7) // 8 * 8
+            ptotal += (int(caps[i]) + 15) // 16 * 16
         pcm = np.empty(ptotal + 64, dtype=np.int16)
         n_samples = np.zeros(len(files), dtype=np.uint64)
         self._check(L.sea_b200_decode_batch(self._h, len(files), sea.ctypes.data, sea_off.ctypes.data, sea_len.ctypes.data,

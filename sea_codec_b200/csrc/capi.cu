@@ -188,13 +188,13 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
     // Descriptor table on the device: [0, n) every chunk of every stream; when the unrolled kernel applies, [n, 2n) the full
     // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
     std::vector<DecStream> table(job.streams);
-    bool unrolled = fast && decode_unrolled_supported(fp) && (reinterpret_cast<uint64_t>(d_pcm) & 15u) == 0;
+    bool unrolled = fast && decode_unrolled_supported(fp) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
     uint64_t chains_a = 0, chains_b = 0;
     if (unrolled) {
         table.resize((size_t)3 * n_streams);
         for (uint32_t i = 0; i < n_streams && unrolled; i++) {
             const DecStream &d = job.streams[i];
-            if (d.pcm_off % 8) unrolled = false;  // TMA stores need 16-byte aligned rows
+            if (d.pcm_off % 16) unrolled = false;  // 256-bit stores need 32-byte aligned rows
             uint64_t n_full = std::min<uint64_t>(d.total_frames / fp.N, d.n_chunks);
             while (n_full > 0 && d.data_off + n_full * fp.chunk_size + 128 > sea_len) n_full--;
             DecStream a = d, b = d;

@@ -9,14 +9,16 @@
 //     warp owns 32 consecutive chunks, one CTA per SM;
 //   * a round is RF frames with RF*C*B a multiple of 32 bits, so every field position inside a round is a compile-time
 //     constant: a field costs one shift and one LOP3 that also forms the look-up address;
-//   * packed residuals are staged word-major ([word][chunk row]) by 4-byte cp.async one round ahead, so "word w of every row"
-//     is one conflict-free shared-memory wavefront; the byte phase of the unaligned section is undone by the same PRMT that
-//     swaps to big-endian;
+//   * every lane stages its own chunk row: 16-byte cp.async granules one round ahead into a row-major tile whose pitch is an
+//     odd number of granules (conflict-free 128-bit writes); the window words are then read at a per-round word offset and the
+//     byte phase of the unaligned section is undone by the same PRMT that swaps to big-endian;
 //   * the dequant row table is replicated per bank (lane l reads bank l) when it fits: the one dependent shared load per
 //     sample is conflict free;
-//   * PCM goes straight from registers to global memory, 16 bytes (4 stereo frames / 8 mono frames) per lane per store: the
-//     output never touches shared memory.  (Earlier variants staged it: TMA bulk stores cost ~6 ALU instructions per sample in
-//     elect/broadcast loops, an STS.U16 + LDS/STG tile copy saturated the shared-memory pipe at 85 %.)
+//   * PCM goes straight from registers to global memory with 256-bit stores (8 stereo / 16 mono frames = one full 32-byte
+//     sector per lane per store), so the output never touches shared memory and costs the L1 tag stage no more than a coalesced
+//     store would.  (Earlier variants: TMA bulk stores cost ~6 ALU instructions per sample in elect/broadcast loops; an
+//     STS.U16 + LDS/STG tile copy saturated the shared-memory pipe at 85 %; 4-byte cp.async and 16-byte stores per lane hit
+//     32 sectors per instruction and choked the L1 tag stage.)
 #include "sea_kernels.h"
 
 namespace sea {
@@ -25,9 +27,15 @@ namespace {
 
 __device__ __forceinline__ void report_f(int *err, int code) { atomicCAS(err, 0, code); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_global_256(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -61,8 +69,11 @@ struct UCfg {
     static constexpr int kHalfBits = HF * C * B;
     static constexpr int kNW = ((kHalfBits + 31 + 31) >> 5);  // big-endian words one half can touch (start offset <= 31 bits)
     static constexpr int kInWords = (((kHalves - 1) * kHalfBits) >> 5) + kNW + 1;  // + one raw word for the byte realign
-    static constexpr int kWarpBytes = 2 * kInWords * kRows * 4;                    // double buffered [word][row]
-    static constexpr int kOutFrames = 8 / C;                  // frames per 16-byte store
+    static constexpr int kInGranRaw = (12 + 4 * kInWords + 15) / 16;               // 16-byte granules incl. alignment slack
+    static constexpr int kInGran = (kInGranRaw % 2) ? kInGranRaw : kInGranRaw + 1; // odd pitch: 8 rows tile all bank groups
+    static constexpr int kInPitch = kInGran * 16;
+    static constexpr int kWarpBytes = 2 * kRows * kInPitch;                        // double buffered [row][pitch]
+    static constexpr int kOutFrames = 16 / C;                 // frames per 32-byte store
     // warps per CTA (one CTA per SM): as many as fit next to <= 33 KB of table, registers allowing (<= 24), multiple of 4
     static constexpr int kWarpsFit = (190 * 1024 / kWarpBytes) / 4 * 4;
     static constexpr int kWarps = kWarpsFit < 24 ? kWarpsFit : 24;
@@ -98,7 +109,7 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     __syncthreads();
     const uint32_t lut_sh = lut_abs + (REPL ? lane * 4u : 0u);
 
-    uint8_t *in_words = smem + warp * Cfg::kWarpBytes;  // [2][kInWords][32 rows]
+    uint8_t *in_rows = smem + warp * Cfg::kWarpBytes;  // [2][32 rows][kInPitch]
 
     uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + lane;  // global chunk index
     const bool valid = g < p.total_chunks;
@@ -127,7 +138,7 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint64_t sf_off = ck_off + 4u + 16u * C;
     const uint64_t res_off = sf_off + div_ceil_u32(items * s, 8u);
     const uint8_t *sfp = sea + sf_off;
-    uint4 *out = reinterpret_cast<uint4 *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
+    uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
 
     // byte phase of the residual section inside a 32-bit word: the same in every round (kRoundBytes % 4 == 0)
     const uint32_t prmt_sel = 0x0123u + ((uint32_t)res_off & 3u) * 0x1111u;  // byte swap + byte realign in one PRMT
@@ -135,13 +146,13 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint32_t n_rounds = p.N / Cfg::RF;
     constexpr int kBlocks = Cfg::RF / Cfg::F;
 
-    // Each lane fetches its own row's next slice word by word into the word-major tile, one round ahead.
-    const uint32_t my_in_sh = smem_u32(in_words) + lane * 4u;
+    // Each lane fetches its own row's next slice as 16-byte granules, one round ahead.
+    const uint32_t my_in_sh = smem_u32(in_rows) + lane * Cfg::kInPitch;
     auto issue_round = [&](uint32_t r) {
-        const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)3);
-        const uint32_t dst = my_in_sh + (r & 1u) * (Cfg::kInWords * Cfg::kRows * 4);
+        const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)15);
+        const uint32_t dst = my_in_sh + (r & 1u) * (Cfg::kRows * Cfg::kInPitch);
 #pragma unroll
-        for (int t = 0; t < Cfg::kInWords; t++) cp_async4(dst + t * Cfg::kRows * 4, src + t * 4);
+        for (int t = 0; t < Cfg::kInGranRaw; t++) cp_async16(dst + t * 16, src + t * 16);
         cp_async_commit();
     };
     // scale-factor bytes are prefetched one round ahead too (they come straight from global memory): one byte pair per field
@@ -166,7 +177,8 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
         if (r + 1 < n_rounds) issue_round(r + 1);
         else cp_async_commit();
         cp_async_wait1();
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_words + (r & 1u) * (Cfg::kInWords * Cfg::kRows * 4)) + lane;
+        const uint32_t bo = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & 12u;  // word offset of the round inside its granule
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_rows + (r & 1u) * (Cfg::kRows * Cfg::kInPitch) + lane * Cfg::kInPitch + bo);
 
         // scale factors of this round's blocks (bytes fetched during the previous round), then prefetch the next round's
         uint32_t sfv[kSfFields];
@@ -186,11 +198,11 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
             constexpr int kNW = Cfg::kNW;
             uint32_t V[kNW + 1], W[kNW];
 #pragma unroll
-            for (int t = 0; t < kNW + 1; t++) V[t] = words[(wlo + t) * Cfg::kRows];
+            for (int t = 0; t < kNW + 1; t++) V[t] = words[wlo + t];
 #pragma unroll
             for (int t = 0; t < kNW; t++) W[t] = __byte_perm(V[t], V[t + 1], prmt_sel);
 
-            uint32_t ow[4];  // 16 bytes of interleaved PCM being assembled
+            uint32_t ow[8];  // 32 bytes of interleaved PCM being assembled
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 uint32_t rowbase[C];
@@ -223,16 +235,16 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
                         h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
                         sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = (y[c] >> 31) | 1;
                     }
-                    // interleaved i16 PCM: 4 stereo frames or 8 mono frames fill one 16-byte store
+                    // interleaved i16 PCM: 8 stereo frames or 16 mono frames fill one 32-byte (full sector) store
                     const int fa = hh * Cfg::HF + fi;  // frame inside the round
                     if (C == 2) {
-                        ow[fa & 3] = __byte_perm((uint32_t)y[0], (uint32_t)y[C - 1], 0x5410);
+                        ow[fa & 7] = __byte_perm((uint32_t)y[0], (uint32_t)y[C - 1], 0x5410);
                     } else {
-                        if ((fa & 1) == 0) ow[(fa >> 1) & 3] = (uint32_t)y[0] & 0xffffu;
-                        else ow[(fa >> 1) & 3] = __byte_perm(ow[(fa >> 1) & 3], (uint32_t)y[0], 0x5410);
+                        if ((fa & 1) == 0) ow[(fa >> 1) & 7] = (uint32_t)y[0] & 0xffffu;
+                        else ow[(fa >> 1) & 7] = __byte_perm(ow[(fa >> 1) & 7], (uint32_t)y[0], 0x5410);
                     }
                     if ((fa % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid)
-                        out[(size_t)r * (Cfg::RF / Cfg::kOutFrames) + fa / Cfg::kOutFrames] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        st_global_256(out + ((size_t)r * (Cfg::RF / Cfg::kOutFrames) + fa / Cfg::kOutFrames) * 32, ow);
                 }
             }
         }
