@@ -353,3 +353,28 @@ def test_device_resident_batch_and_properties(ctx, oracle):
         assert np.array_equal(dec[i], dec[i % 4])
     err = dec[:4].astype(np.float64) - pcm[:4].cpu().numpy()
     assert np.sqrt(np.mean((err / 32767.0) ** 2)) < 0.05
+
+
+def test_cpp_host_mirror(ctx, oracle, tmp_path):
+    """include/sea_b200.hpp (the compiled-language host mirror of src/encoder.rs, src/decoder.rs, src/lib.rs) driven the way
+    tests/streaming.rs drives the crate: one-shot encode, chunk-at-a-time SeaEncoder, SeaDecoder over the result."""
+    import subprocess
+
+    from sea_codec_b200 import build as B
+
+    exe = os.path.join(ROOT, "tests", "build", "host_mirror_test")
+    src = os.path.join(ROOT, "tests", "csrc", "host_mirror_test.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    lib_dir = os.path.dirname(B.LIB)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, src, "-L" + lib_dir, "-l:libsea_b200.so", "-Wl,-rpath," + lib_dir], check=True)
+    for channels, bits, vbr in ((2, 3.0, 0), (1, 3.0, 1), (3, 5.0, 0)):
+        pcm = synth.gen_stream(50 + channels, 5120 * 2 + 777, channels, 44100)
+        raw = tmp_path / "in.raw"
+        raw.write_bytes(pcm.astype("<i2").tobytes())
+        one, stream, dec = tmp_path / "one.sea", tmp_path / "stream.sea", tmp_path / "dec.raw"
+        r = subprocess.run([exe, str(raw), str(channels), "44100", str(bits), str(vbr), str(one), str(stream), str(dec)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        ref = oracle.sea_encode(pcm, 44100, channels, oracle.make_settings(bits, bool(vbr)))
+        assert one.read_bytes() == ref and stream.read_bytes() == ref
+        assert np.array_equal(np.frombuffer(dec.read_bytes(), dtype="<i2"), oracle.sea_decode(ref).samples)
