@@ -188,6 +188,144 @@ __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------- fast search pass
+// Same result as search_pass for scale_factor_bits = 4 (one candidate per lane, two chains per warp), organised around what
+// the profile of the generic pass showed (profiles/r01_encode_generic_v1_*): 95 % of the stall samples sat on the global load of
+// the PCM sample inside the 20-step recurrence.  Here the block's samples are staged through shared memory one block ahead, the
+// dequant rows live in shared memory as [size][code][sf] (the lane's sf is fixed), FB > 0 makes the residual size a compile-time
+// constant, and err^2 / penalty^2 are accumulated with 64-bit fused multiply-adds.
+struct FastLut {
+    const int32_t *lut;     // shared memory
+    uint32_t slot_off[4];   // word offset of the table of size lo_size + i
+    uint32_t lo_size;
+};
+
+template <int FB>
+__device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParams &p, const int16_t *__restrict__ x0, uint32_t frames,
+                                 const int32_t *__restrict__ tab, int32_t *st_w, int32_t *st_h, int32_t *st_prev, uint8_t *codes,
+                                 uint32_t *chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs, const FastLut &fl,
+                                 int16_t *xbuf_all)
+{
+    constexpr uint32_t s = 4, nsf = 16, lpc = 16, cpw = 2;
+    const uint32_t C = p.channels, F = p.F;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t grp = lane >> 4, sf = lane & 15u;
+    const uint32_t slots = nwarps * cpw;
+    const uint32_t T = blockDim.x;
+    const uint32_t nblk = div_ceil_u32(frames, F);
+    int16_t *xbuf = xbuf_all + warp * (cpw * F);  // [chain group][frame]
+
+    for (uint32_t cb = warp * cpw; cb < C; cb += slots) {  // warp-uniform: this warp's pair of channels
+        const uint32_t c_raw = cb + grp;
+        const bool active = c_raw < C;
+        const uint32_t c = active ? c_raw : C - 1u;
+        // stage block 0: lane l < F brings frame l of both chains
+        {
+            const uint32_t nf0 = frames < F ? frames : F;
+            if (lane < nf0) {
+                const int16_t *px = x0 + (uint64_t)lane * C;
+                xbuf[lane] = __ldg(px + cb);
+                xbuf[F + lane] = __ldg(px + (cb + 1u < C ? cb + 1u : C - 1u));
+            }
+        }
+        __syncwarp();
+        for (uint32_t blk = 0; blk < nblk; blk++) {
+            uint32_t nf = frames - blk * F;
+            if (nf > F) nf = F;
+            // prefetch the next block's samples into registers; they land in shared memory after this block's steps
+            int32_t nx0 = 0, nx1 = 0;
+            const uint32_t next_frame = (blk + 1u) * F + lane;
+            const bool pre = blk + 1u < nblk && lane < F && next_frame < frames;
+            if (pre) {
+                const int16_t *px = x0 + (uint64_t)next_frame * C;
+                nx0 = __ldg(px + cb);
+                nx1 = __ldg(px + (cb + 1u < C ? cb + 1u : C - 1u));
+            }
+            const uint32_t size = FB > 0 ? (uint32_t)FB : (mode == 2 ? (uint32_t)vs.sizes[blk * C + c] : uniform_size);
+            const int32_t recip = __ldg(tab + tab_recip_off(s, size) + sf);
+            const int32_t *row = fl.lut + fl.slot_off[FB > 0 ? 0 : size - fl.lo_size] + sf;
+            const uint32_t kmax = (1u << (size - 1u)) - 1u;
+
+            int32_t w[4], h[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                w[i] = st_w[c * 4 + i];
+                h[i] = st_h[c * 4 + i];
+            }
+            const uint32_t prev = (uint32_t)st_prev[c];
+            const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
+            unsigned long long rank = 0;
+            const int16_t *xs = xbuf + grp * F;
+            uint8_t *cbuf = codes + threadIdx.x;
+#pragma unroll 4
+            for (uint32_t f = 0; f < nf; f++) {  // encoder_base.rs:64-89
+                const int32_t xv = xs[f];
+                const int32_t pr = lms_predict(w, h);
+                const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
+                const int32_t n = (int32_t)(((int64_t)r * (int64_t)recip + 32768) >> 16);
+                const uint32_t an = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;
+                uint32_t k = an >> 1;
+                k = k < kmax ? k : kmax;
+                if ((FB > 0 ? (uint32_t)FB : size) == 2u) k = an >= 3u ? 1u : 0u;
+                const uint32_t code = 2u * k + ((uint32_t)r >> 31);
+                const int32_t d = row[code << 4];
+                const int32_t y = clamp_i16((int32_t)((uint32_t)pr + (uint32_t)d));
+                const int32_t e = xv - y;
+                rank += (unsigned long long)((long long)e * e) + lms_penalty(w);
+                lms_update(w, h, y, d);
+                cbuf[(size_t)f * T] = (uint8_t)code;
+            }
+            // arg-min over the 16 candidates of the chain: strict total order (rank, ord)
+            unsigned long long g_rank = rank;
+            uint32_t g_ord = ord, g_lane = lane;
+#pragma unroll
+            for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
+                const unsigned long long o_rank = __shfl_xor_sync(0xffffffffu, g_rank, o);
+                const uint32_t o_ord = __shfl_xor_sync(0xffffffffu, g_ord, o);
+                const uint32_t o_lane = __shfl_xor_sync(0xffffffffu, g_lane, o);
+                if (o_rank < g_rank || (o_rank == g_rank && o_ord < g_ord)) {
+                    g_rank = o_rank;
+                    g_ord = o_ord;
+                    g_lane = o_lane;
+                }
+            }
+            if (active && lane == g_lane) {  // encoder_base.rs:181-186: persist the winner
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    st_w[c * 4 + i] = w[i];
+                    st_h[c * 4 + i] = h[i];
+                }
+                st_prev[c] = (int32_t)sf;
+                if (mode == 1) vs.keys[blk * C + c] = rank;
+                else put_bits(chunk_buf, sf_sec_bit + (blk * C + c) * s, s, sf);
+            }
+            if (mode != 1 && active) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
+                uint32_t blockbit, rowbits, prefix;
+                if (mode == 2) {
+                    blockbit = vs.blkbit[blk];
+                    rowbits = vs.rowbits[blk];
+                    prefix = 0;
+                    for (uint32_t cc = 0; cc < c; cc++) prefix += vs.sizes[blk * C + cc];
+                } else {
+                    rowbits = C * size;
+                    blockbit = blk * F * rowbits;
+                    prefix = c * size;
+                }
+                const uint8_t *wbuf = codes + (threadIdx.x - lane + g_lane);
+                for (uint32_t f = sf; f < nf; f += lpc)
+                    put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[(size_t)f * T]);
+            }
+            __syncwarp();  // everybody is done with this block's samples, codes and state
+            if (pre) {
+                xbuf[lane] = (int16_t)nx0;
+                xbuf[F + lane] = (int16_t)nx1;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // CTA-wide bitonic sort of (key, idx) pairs, ascending; idx breaks ties (SURVEY trap T13).
 __device__ void bitonic_sort(unsigned long long *keys, uint32_t *idx, uint32_t n)
 {
@@ -213,9 +351,11 @@ __device__ void bitonic_sort(unsigned long long *keys, uint32_t *idx, uint32_t n
     }
 }
 
-__global__ void encode_generic_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out,
-                                      const EncStream *__restrict__ streams, EncParams p, DevTables tabs, int32_t *state,
-                                      uint64_t *out_lens, uint32_t *chunk0, unsigned long long *ties, EncWorkspace ws, int *err)
+// FB = -1: generic search pass (any scale_factor_bits);  FB = 0: fast pass, runtime residual sizes (VBR);  FB = 1..8: fast pass, CBR.
+template <int FB>
+__global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const EncStream *__restrict__ streams,
+                              EncParams p, DevTables tabs, int32_t *state, uint64_t *out_lens, uint32_t *chunk0,
+                              unsigned long long *ties, EncWorkspace ws, int *err)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t sidx = blockIdx.x;
@@ -232,6 +372,27 @@ __global__ void encode_generic_kernel(const int16_t *__restrict__ pcm, uint8_t *
     int32_t *sv_h = sv_w + 4 * C;
     uint8_t *codes = reinterpret_cast<uint8_t *>(sv_h + 4 * C);
     __shared__ uint32_t sh_res_bits;
+    // fast pass extras: per-warp sample staging and the dequant tables [size][code][sf]
+    FastLut fl = {};
+    int16_t *xbuf = nullptr;
+    if (FB >= 0) {
+        uint8_t *extra = codes + ((2u * (size_t)F * T + 15u) & ~(size_t)15u);
+        xbuf = reinterpret_cast<int16_t *>(extra);
+        int32_t *lut = reinterpret_cast<int32_t *>(extra + (((T >> 5) * 2u * F * 2u + 15u) & ~15u));
+        fl.lut = lut;
+        fl.lo_size = FB > 0 ? (uint32_t)FB : (p.base > 1u ? p.base - 1u : 1u);
+        const uint32_t n_slots = FB > 0 ? 1u : 4u;
+        uint32_t off = 0;
+        for (uint32_t i = 0; i < n_slots; i++) {
+            const uint32_t size = fl.lo_size + i;
+            fl.slot_off[i] = off;
+            if (size <= 8u) {
+                const uint32_t n = 16u << size;
+                for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 4)];
+                off += n;
+            }
+        }
+    }
 
     VbrScratch vs = {};
     if (p.vbr) vs = carve_scratch(ws.vbr_scratch + (uint64_t)sidx * ws.vbr_scratch_stride, p);
@@ -294,11 +455,13 @@ __global__ void encode_generic_kernel(const int16_t *__restrict__ pcm, uint8_t *
         }
 
         if (!p.vbr) {
-            search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (FB >= 0) search_pass_fast<FB>(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            else search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
             if (tid == 0) sh_res_bits = frames * C * p.hdr_bits;
         } else {
             // ---- analysis at base+1 bits (encoder_vbr.rs:139-171); restores lms only (trap T2)
-            search_pass(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (FB >= 0) search_pass_fast<FB>(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            else search_pass(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
             __syncthreads();
             for (uint32_t i = tid; i < 4 * C; i += T) {
                 st_w[i] = sv_w[i];
@@ -352,7 +515,8 @@ __global__ void encode_generic_kernel(const int16_t *__restrict__ pcm, uint8_t *
                 put_bits(chunk_buf, vbr_sec_bit + 2u * i, 2u, ((uint32_t)vs.sizes[i] - p.hdr_bits + 1u) & 3u);
             __syncthreads();
             // ---- second pass with the chosen sizes (encoder_vbr.rs:193-207)
-            search_pass(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (FB >= 0) search_pass_fast<FB>(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            else search_pass(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
         }
         __syncthreads();
 
@@ -395,6 +559,17 @@ __global__ void encode_generic_kernel(const int16_t *__restrict__ pcm, uint8_t *
     }
 }
 
+template <int FB>
+static cudaError_t launch_encode_t(const int16_t *d_pcm, uint8_t *d_out, const EncStream *d_streams, const EncParams &p, DevTables tabs,
+                                   int32_t *d_state, uint64_t *d_out_lens, uint32_t *d_chunk0, unsigned long long *d_ties, EncWorkspace ws,
+                                   int *d_err, cudaStream_t stream, uint32_t T, size_t smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(encode_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_kernel<FB><<<p.n_streams, T, smem, stream>>>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const EncStream *d_streams, const EncParams &p,
                                   DevTables tabs, int32_t *d_state, uint64_t *d_out_lens, uint32_t *d_chunk0,
                                   unsigned long long *d_ties, EncWorkspace ws, int *d_err, cudaStream_t stream)
@@ -405,13 +580,34 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     if (warps > 8u) warps = 8u;
     if (p.vbr && warps < 4u) warps = 4u;  // the sort and the section writers are CTA-wide
     const uint32_t T = warps * 32u;
-    const size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + 2u * (size_t)p.F * T + 16u;
+    size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + ((2u * (size_t)p.F * T + 15u) & ~(size_t)15u) + 16u;
+    // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
+    const bool fast = p.s == 4u && p.F <= 32u && p.channels <= 16u;
+    if (fast) {
+        smem += ((size_t)warps * 2u * p.F * 2u + 15u) & ~(size_t)15u;
+        if (p.vbr) {
+            const uint32_t lo = p.base > 1u ? p.base - 1u : 1u;
+            for (uint32_t i = 0; i < 4u; i++)
+                if (lo + i <= 8u) smem += (size_t)(16u << (lo + i)) * 4u;
+        } else {
+            smem += (size_t)(16u << p.hdr_bits) * 4u;
+        }
+    }
     if (smem > 200u * 1024u) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(encode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    encode_generic_kernel<<<p.n_streams, T, smem, stream>>>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties,
-                                                          ws, d_err);
-    return cudaGetLastError();
+#define SEA_ENC(FBV) return launch_encode_t<FBV>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err, stream, T, smem)
+    if (!fast) SEA_ENC(-1);
+    if (p.vbr) SEA_ENC(0);
+    switch (p.hdr_bits) {
+        case 1: SEA_ENC(1);
+        case 2: SEA_ENC(2);
+        case 3: SEA_ENC(3);
+        case 4: SEA_ENC(4);
+        case 5: SEA_ENC(5);
+        case 6: SEA_ENC(6);
+        case 7: SEA_ENC(7);
+        default: SEA_ENC(8);
+    }
+#undef SEA_ENC
 }
 
 }  // namespace sea
