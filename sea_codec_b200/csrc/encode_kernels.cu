@@ -195,8 +195,14 @@ __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p,
 // the PCM sample inside the 20-step recurrence.  Here the block's samples are staged through shared memory one block ahead, the
 // dequant rows live in shared memory as [size][code][sf] (the lane's sf is fixed), FB > 0 makes the residual size a compile-time
 // constant, and err^2 / penalty^2 are accumulated with 64-bit fused multiply-adds.
+template <bool V>
+struct NarrowTag {
+    static constexpr bool value = V;
+};
+
 struct FastLut {
-    const int32_t *lut;     // shared memory
+    const int32_t *lut;     // shared memory: per size a table [code][32 lanes] (lane & 15 = scale factor)
+    const int32_t *recip;   // shared memory: [slot][16]
     uint32_t slot_off[4];   // word offset of the table of size lo_size + i
     uint32_t lo_size;
 };
@@ -243,8 +249,9 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 nx1 = __ldg(px + (cb + 1u < C ? cb + 1u : C - 1u));
             }
             const uint32_t size = FB > 0 ? (uint32_t)FB : (mode == 2 ? (uint32_t)vs.sizes[blk * C + c] : uniform_size);
-            const int32_t recip = __ldg(tab + tab_recip_off(s, size) + sf);
-            const int32_t *row = fl.lut + fl.slot_off[FB > 0 ? 0 : size - fl.lo_size] + sf;
+            const uint32_t slot = FB > 0 ? 0u : size - fl.lo_size;
+            const int32_t recip = fl.recip[slot * 16u + sf];
+            const int32_t *row = fl.lut + fl.slot_off[slot] + lane;  // [code][lane]: both chains of the warp read their own banks
             const uint32_t kmax = (1u << (size - 1u)) - 1u;
 
             int32_t w[4], h[4];
@@ -258,24 +265,29 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             unsigned long long rank = 0;
             const int16_t *xs = xbuf + grp * F;
             uint8_t *cbuf = codes + threadIdx.x;
+            // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
+            auto trial = [&](auto narrow_tag) {
+                constexpr bool kNarrow = decltype(narrow_tag)::value;
 #pragma unroll 4
-            for (uint32_t f = 0; f < nf; f++) {  // encoder_base.rs:64-89
-                const int32_t xv = xs[f];
-                const int32_t pr = lms_predict(w, h);
-                const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
-                const int32_t n = (int32_t)(((int64_t)r * (int64_t)recip + 32768) >> 16);
-                const uint32_t an = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;
-                uint32_t k = an >> 1;
-                k = k < kmax ? k : kmax;
-                if ((FB > 0 ? (uint32_t)FB : size) == 2u) k = an >= 3u ? 1u : 0u;
-                const uint32_t code = 2u * k + ((uint32_t)r >> 31);
-                const int32_t d = row[code << 4];
-                const int32_t y = clamp_i16((int32_t)((uint32_t)pr + (uint32_t)d));
-                const int32_t e = xv - y;
-                rank += (unsigned long long)((long long)e * e) + lms_penalty(w);
-                lms_update(w, h, y, d);
-                cbuf[(size_t)f * T] = (uint8_t)code;
-            }
+                for (uint32_t f = 0; f < nf; f++) {
+                    const int32_t xv = xs[f];
+                    const int32_t pr = lms_predict(w, h);
+                    const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
+                    const int32_t n = (int32_t)(((int64_t)r * (int64_t)recip + 32768) >> 16);
+                    const uint32_t an = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;
+                    uint32_t k = an >> 1;
+                    k = k < kmax ? k : kmax;
+                    if ((FB > 0 ? (uint32_t)FB : size) == 2u) k = an >= 3u ? 1u : 0u;
+                    const uint32_t code = 2u * k + ((uint32_t)r >> 31);
+                    const int32_t d = row[code << 5];
+                    const int32_t y = clamp_i16((int32_t)((uint32_t)pr + (uint32_t)d));
+                    rank = rank_step<kNarrow>(rank, xv - y, w);
+                    lms_update(w, h, y, d);
+                    cbuf[(size_t)f * T] = (uint8_t)code;
+                }
+            };
+            if (__all_sync(0xffffffffu, weights_stay_narrow(w, F))) trial(NarrowTag<true>{});
+            else trial(NarrowTag<false>{});
             // arg-min over the 16 candidates of the chain: strict total order (rank, ord)
             unsigned long long g_rank = rank;
             uint32_t g_ord = ord, g_lane = lane;
@@ -378,8 +390,10 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
     if (FB >= 0) {
         uint8_t *extra = codes + ((2u * (size_t)F * T + 15u) & ~(size_t)15u);
         xbuf = reinterpret_cast<int16_t *>(extra);
-        int32_t *lut = reinterpret_cast<int32_t *>(extra + (((T >> 5) * 2u * F * 2u + 15u) & ~15u));
+        int32_t *rcp = reinterpret_cast<int32_t *>(extra + (((T >> 5) * 2u * F * 2u + 15u) & ~15u));
+        int32_t *lut = rcp + 64;
         fl.lut = lut;
+        fl.recip = rcp;
         fl.lo_size = FB > 0 ? (uint32_t)FB : (p.base > 1u ? p.base - 1u : 1u);
         const uint32_t n_slots = FB > 0 ? 1u : 4u;
         uint32_t off = 0;
@@ -387,15 +401,16 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
             const uint32_t size = fl.lo_size + i;
             fl.slot_off[i] = off;
             if (size <= 8u) {
-                const uint32_t n = 16u << size;
-                for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 4)];
+                const uint32_t n = 32u << size;
+                for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 5)];
+                for (uint32_t e = tid; e < 16u; e += T) rcp[i * 16u + e] = tab[tab_recip_off(4, size) + e];
                 off += n;
             }
         }
     }
 
     VbrScratch vs = {};
-    if (p.vbr) vs = carve_scratch(ws.vbr_scratch + (uint64_t)sidx * ws.vbr_scratch_stride, p);
+    if (p.vbr) vs = carve_scratch(p.vbr_smem_off ? smem + p.vbr_smem_off : ws.vbr_scratch + (uint64_t)sidx * ws.vbr_scratch_stride, p);
 
     // EncoderBase::new (encoder_base.rs:29-41, lms.rs:19-32) or the state kept by a streaming handle
     for (uint32_t c = tid; c < C; c += T) {
@@ -578,7 +593,6 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     const uint32_t nsf = 1u << p.s, lpc = nsf < 32u ? nsf : 32u, cpw = 32u / lpc;
     uint32_t warps = (p.channels + cpw - 1u) / cpw;
     if (warps > 8u) warps = 8u;
-    if (p.vbr && warps < 4u) warps = 4u;  // the sort and the section writers are CTA-wide
     const uint32_t T = warps * 32u;
     size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + ((2u * (size_t)p.F * T + 15u) & ~(size_t)15u) + 16u;
     // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
@@ -588,13 +602,24 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
         if (p.vbr) {
             const uint32_t lo = p.base > 1u ? p.base - 1u : 1u;
             for (uint32_t i = 0; i < 4u; i++)
-                if (lo + i <= 8u) smem += (size_t)(16u << (lo + i)) * 4u;
+                if (lo + i <= 8u) smem += (size_t)(32u << (lo + i)) * 4u;
         } else {
-            smem += (size_t)(16u << p.hdr_bits) * 4u;
+            smem += (size_t)(32u << p.hdr_bits) * 4u;
+        }
+        smem += 64u * 4u;  // reciprocals [slot][16]
+    }
+    EncParams pp = p;
+    pp.vbr_smem_off = 0;
+    if (p.vbr) {  // keep the per-chunk VBR scratch in shared memory when it is small (stereo: 8.7 KB)
+        const uint64_t sc = enc_vbr_scratch_bytes(p);
+        if (sc <= 40u * 1024u && smem + sc + 16u <= 200u * 1024u) {
+            smem = (smem + 15u) & ~(size_t)15u;
+            pp.vbr_smem_off = (uint32_t)smem;
+            smem += sc;
         }
     }
     if (smem > 200u * 1024u) return cudaErrorInvalidConfiguration;
-#define SEA_ENC(FBV) return launch_encode_t<FBV>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err, stream, T, smem)
+#define SEA_ENC(FBV) return launch_encode_t<FBV>(d_pcm, d_out, d_streams, pp, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err, stream, T, smem)
     if (!fast) SEA_ENC(-1);
     if (p.vbr) SEA_ENC(0);
     switch (p.hdr_bits) {

@@ -63,6 +63,33 @@ SEA_HD uint64_t lms_penalty(const int32_t w[4])
     return q * q;
 }
 
+// rank += err^2 + penalty(w), exactly as encoder_base.rs:78-82 with lms.rs:53-62 (wrapping u64).
+// NARROW = true is valid while every |w[i]| < 2^23 (then sum(w^2) < 2^48, the shifted sum fits 31 bits and the square is one
+// 32x32->64 multiply-add); callers establish that bound once per block, not per sample.
+template <bool NARROW>
+SEA_HD uint64_t rank_step(uint64_t rank, int32_t err, const int32_t w[4])
+{
+    const uint64_t sum = (uint64_t)((int64_t)w[0] * w[0]) + (uint64_t)((int64_t)w[1] * w[1]) + (uint64_t)((int64_t)w[2] * w[2]) +
+                         (uint64_t)((int64_t)w[3] * w[3]);
+    rank += (uint64_t)((int64_t)err * (int64_t)err);
+    if (NARROW) {
+        int32_t t = (int32_t)(uint32_t)(sum >> 18) - 0x8ff;
+        t = t > 0 ? t : 0;
+        return rank + (uint64_t)(uint32_t)t * (uint64_t)(uint32_t)t;
+    }
+    const int64_t p = ((int64_t)sum >> 18) - 0x8ff;
+    const uint64_t q = p > 0 ? (uint64_t)p : 0;
+    return rank + q * q;
+}
+// a weight moves by at most |d >> 4| <= 1578 per sample (|d| <= 255 * 99, dqt.rs) -> bound over a block of F samples
+SEA_HD bool weights_stay_narrow(const int32_t w[4], uint32_t F)
+{
+    const int32_t lim = (1 << 23) - 1 - (int32_t)F * 1600;
+    bool ok = true;
+    for (int i = 0; i < 4; i++) ok = ok && w[i] < lim && w[i] > -lim;
+    return ok;
+}
+
 // encoder_base.rs:22-26 (sea_div) + :71-72 (clamp, SeaQuantTab lookup) as one closed form.
 //   n = (r*recip + 2^15) >> 16 (i64, floor);  scaled = n + (sgn(r) - sgn(n)).
 // Because recip > 0, n never has the opposite sign of r; the fix-up only turns 0 into sgn(r), which does not

@@ -66,6 +66,7 @@ struct EncParams {
     uint32_t sample_rate;
     uint32_t raw_chunk_mode;   // 1: write only the chunk at out_off, no file header (make_chunk seam)
     uint32_t n_streams;
+    uint32_t vbr_smem_off;     // != 0: the VBR scratch (ranks, sort keys, sizes) lives in shared memory at this offset
 };
 
 // Persistent per-channel encoder state (EncoderBase.lms + prev_scalefactor, encoder_base.rs:15-19): 9 int32 per channel

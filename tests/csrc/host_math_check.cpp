@@ -9,3 +9,10 @@ void hm_update(int *w, int *h, int y, int d) { sea::lms_update(w, h, y, d); }
 unsigned long long hm_penalty(const int *w) { return sea::lms_penalty(w); }
 int hm_clamp(int v) { return sea::clamp_i16(v); }
 }
+extern "C" unsigned long long hm_rank_step(unsigned long long rank, int err, const int *w)
+{
+    // the narrow form must agree with the wide one wherever its precondition holds
+    unsigned long long wide = sea::rank_step<false>(rank, err, w);
+    if (sea::weights_stay_narrow(w, 0) && sea::rank_step<true>(rank, err, w) != wide) return ~wide;
+    return wide;
+}

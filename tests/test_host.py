@@ -151,6 +151,11 @@ def test_lms_arithmetic_matches_definition():
         ssum = ssum - (1 << 64) if ssum >= (1 << 63) else ssum
         pen = max(0, (ssum >> 18) - 0x8FF)
         assert H.hm_penalty(w.ctypes.data) == (pen * pen) & 0xFFFFFFFFFFFFFFFF
+        err = int(rng.integers(-65535, 65536))
+        rank0 = int(rng.integers(0, 2**62))
+        H.hm_rank_step.restype = C.c_ulonglong
+        H.hm_rank_step.argtypes = [C.c_ulonglong, C.c_int, C.c_void_p]
+        assert H.hm_rank_step(rank0, err, w.ctypes.data) == (rank0 + err * err + pen * pen) & 0xFFFFFFFFFFFFFFFF
         d = int(rng.integers(-30000, 30000))
         y = int(rng.integers(-32768, 32768))
         w2, h2 = w.copy(), h.copy()
