@@ -143,9 +143,9 @@ def lib() -> C.CDLL:
     """Loads (building first when the sources are newer) sea_codec_b200/libsea_b200.so.  Fails loudly if absent."""
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("SEA_B200_LIB") or _build.LIB  # override: a tuning build of the same C-ABI (tools/build_variant.py)
         try:
-            if _build.is_stale():
+            if path == _build.LIB and _build.is_stale():
                 _build.build()
         except Exception as e:  # no nvcc on this box: use the prebuilt library if there is one
             if not os.path.exists(path):

@@ -37,16 +37,17 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: str = LIB, build_dir: str | None = None) -> str:
+    """extra_flags / lib_path / build_dir: tuning builds (tools/build_variant.py) next to the product library."""
+    if not force and not is_stale() and lib_path == LIB:
         return LIB
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = build_dir or os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for s in SOURCES:
         obj = os.path.join(build_dir, os.path.splitext(s)[0] + ".o")
-        cmd = [nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -59,8 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc(), "-shared", "-o", LIB, *objs, "-cudart", "static"], check=True)
-    return LIB
+    subprocess.run([nvcc(), "-shared", "-o", lib_path, *objs, "-cudart", "static"], check=True)
+    return lib_path
 
 
 if __name__ == "__main__":

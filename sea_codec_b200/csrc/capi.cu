@@ -54,6 +54,8 @@ struct sea_b200_ctx {
     int *d_err = nullptr;
     unsigned long long *d_ties = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side = nullptr;                       // partial-chunk decode runs beside the full-chunk kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string last_error;
     uint64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -226,12 +228,18 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
             DecFastParams fa = fp, fb = fp;
             fa.total_chunks = chains_a / fp.channels;
             fb.total_chunks = chains_b / fp.channels;
+            // The left-over chunks (one partial chunk per stream: a short grid of long serial chains) go first, on the side
+            // stream, so that their latency hides under the full-chunk kernel instead of trailing it.
+            if (fb.total_chunks) {
+                CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+                CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, ctx->d_err, ctx->side));
+                ctx->launches++;
+                CU(cudaEventRecord(ctx->ev_join, ctx->side));
+            }
             CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, ctx->d_err, ctx->stream));
             ctx->launches++;
-            if (fb.total_chunks) {
-                CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, ctx->d_err, ctx->stream));
-                ctx->launches++;
-            }
+            if (fb.total_chunks) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         } else {
             CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all, fp, ctx->tabs, ctx->d_err, ctx->stream));
             ctx->launches++;
@@ -404,6 +412,9 @@ int sea_b200_ctx_create(int device, sea_b200_ctx **out)
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->own_stream = true;
+    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(e);
@@ -435,6 +446,9 @@ void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
     ctx->misc.release();
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->d_ties) cudaFree(ctx->d_ties);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -21,6 +21,13 @@
 //     32 sectors per instruction and choked the L1 tag stage.)
 #include "sea_kernels.h"
 
+#ifndef SEA_DEC_WARPS
+#define SEA_DEC_WARPS 16
+#endif
+#ifndef SEA_DEC_PAIR
+#define SEA_DEC_PAIR 0  // 1: the look-up table holds (d, d >> 4) pairs read with one 64-bit load (saves the shift per sample)
+#endif
+
 namespace sea {
 
 namespace {
@@ -46,6 +53,11 @@ __device__ __forceinline__ int32_t lds_s32(uint32_t addr)
     return v;
 }
 
+__device__ __forceinline__ void lds_s32x2(uint32_t addr, int32_t &a, int32_t &b)
+{
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+}
+
 __device__ __forceinline__ uint32_t find_stream_f(const DecStream *streams, uint32_t n_streams, uint64_t chain)
 {
     uint32_t lo = 0, hi = n_streams;  // last stream whose chain_begin <= chain
@@ -61,22 +73,24 @@ template <int C, int B>
 struct UCfg {
     static constexpr int F = 20;                              // scale_factor_frames this kernel is unrolled for
     static constexpr int kRows = 32;                          // chunks per warp: one per lane
-    static constexpr int RF = ((C * B) % 2 == 0) ? 80 : 160;  // frames per round: RF*C*B % 32 == 0 and RF % F == 0
-    static constexpr int kRoundBits = RF * C * B;
-    static constexpr int kRoundBytes = kRoundBits / 8;
-    static constexpr int HF = 40;                             // frames per window refill (two blocks)
-    static constexpr int kHalves = RF / HF;
-    static constexpr int kHalfBits = HF * C * B;
-    static constexpr int kNW = ((kHalfBits + 31 + 31) >> 5);  // big-endian words one half can touch (start offset <= 31 bits)
-    static constexpr int kInWords = (((kHalves - 1) * kHalfBits) >> 5) + kNW + 1;  // + one raw word for the byte realign
+    static constexpr int HF = 80 / C;                         // frames per unrolled body ("half"): 80 samples, whole blocks
+    static constexpr int kBlk = HF / F;                       // scale-factor blocks per half
+    static constexpr int kHalfBits = HF * C * B;              // a multiple of 8: a half starts on a byte boundary of the section
+    static constexpr int kHalfBytes = kHalfBits / 8;
+    static constexpr int kHalves = 2;                         // halves staged per cp.async round
+    static constexpr int RF = kHalves * HF;                   // frames per round
+    static constexpr int kRoundBytes = kHalves * kHalfBytes;
+    static constexpr int kNW = (kHalfBits + 31) >> 5;         // big-endian words of one half (it starts at bit 0 of W[0])
+    static constexpr int kInWords = ((3 + (kHalves - 1) * kHalfBytes) >> 2) + kNW + 1;  // words a round can touch from its first word
     static constexpr int kInGranRaw = (12 + 4 * kInWords + 15) / 16;               // 16-byte granules incl. alignment slack
     static constexpr int kInGran = (kInGranRaw % 2) ? kInGranRaw : kInGranRaw + 1; // odd pitch: 8 rows tile all bank groups
     static constexpr int kInPitch = kInGran * 16;
-    static constexpr int kWarpBytes = 2 * kRows * kInPitch;                        // double buffered [row][pitch]
+    static constexpr int kBufBytes = kRows * kInPitch + 64;  // rows 8j.. are skewed by j granules: conflict-free 32-bit window reads
+    static constexpr int kWarpBytes = 2 * kBufBytes;          // double buffered [row][pitch]
     static constexpr int kOutFrames = 16 / C;                 // frames per 32-byte store
     // warps per CTA (one CTA per SM): as many as fit next to <= 33 KB of table, registers allowing (<= 24), multiple of 4
     static constexpr int kWarpsFit = (190 * 1024 / kWarpBytes) / 4 * 4;
-    static constexpr int kWarps = kWarpsFit < 24 ? kWarpsFit : 24;
+    static constexpr int kWarps = kWarpsFit < SEA_DEC_WARPS ? kWarpsFit : SEA_DEC_WARPS;
 };
 
 }  // namespace
@@ -93,21 +107,29 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
 
     // ---- dequant rows of residual size B: lut[sf][code], replicated per bank when REPL (entry stride 128 B, lane l at +4l).
     // The table sits after the warp tiles at an address aligned to its own size, so "row base | code offset" never carries.
-    constexpr int kShift = REPL ? 7 : 2;  // log2 of the byte stride between consecutive codes
+    constexpr int kPair = SEA_DEC_PAIR;
+    constexpr int kShift = (REPL ? 7 : 2) + kPair;  // log2 of the byte stride between consecutive codes
     const uint32_t smem_sh = smem_u32(smem);
     const uint32_t lut_abs = (smem_sh + Cfg::kWarps * Cfg::kWarpBytes + lut_align - 1u) & ~(lut_align - 1u);
     int32_t *lut = reinterpret_cast<int32_t *>(smem + (lut_abs - smem_sh));
     {
         const uint32_t entries = 1u << (s + B);
         const int32_t *src = tab + tab_dqt_off(s, B);
-        if (REPL) {
+        if (kPair) {
+            const uint32_t n = REPL ? entries * 32u : entries;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const int32_t d = src[REPL ? (i >> 5) : i];
+                lut[2 * i] = d;
+                lut[2 * i + 1] = d >> 4;  // lms.rs:44
+            }
+        } else if (REPL) {
             for (uint32_t i = threadIdx.x; i < entries * 32u; i += blockDim.x) lut[i] = src[i >> 5];
         } else {
             for (uint32_t i = threadIdx.x; i < entries; i += blockDim.x) lut[i] = src[i];
         }
     }
     __syncthreads();
-    const uint32_t lut_sh = lut_abs + (REPL ? lane * 4u : 0u);
+    const uint32_t lut_sh = lut_abs + (REPL ? (lane * 4u) << kPair : 0u);
 
     uint8_t *in_rows = smem + warp * Cfg::kWarpBytes;  // [2][32 rows][kInPitch]
 
@@ -140,81 +162,107 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint8_t *sfp = sea + sf_off;
     uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
 
-    // byte phase of the residual section inside a 32-bit word: the same in every round (kRoundBytes % 4 == 0)
-    const uint32_t prmt_sel = 0x0123u + ((uint32_t)res_off & 3u) * 0x1111u;  // byte swap + byte realign in one PRMT
-
     const uint32_t n_rounds = p.N / Cfg::RF;
-    constexpr int kBlocks = Cfg::RF / Cfg::F;
 
     // Each lane fetches its own row's next slice as 16-byte granules, one round ahead.
-    const uint32_t my_in_sh = smem_u32(in_rows) + lane * Cfg::kInPitch;
+    const uint32_t my_in_sh = smem_u32(in_rows) + lane * Cfg::kInPitch + (lane >> 3) * 16u;
     auto issue_round = [&](uint32_t r) {
         const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)15);
-        const uint32_t dst = my_in_sh + (r & 1u) * (Cfg::kRows * Cfg::kInPitch);
+        const uint32_t dst = my_in_sh + (r & 1u) * Cfg::kBufBytes;
 #pragma unroll
         for (int t = 0; t < Cfg::kInGranRaw; t++) cp_async16(dst + t * 16, src + t * 16);
         cp_async_commit();
     };
-    // scale-factor bytes are prefetched one round ahead too (they come straight from global memory): one byte pair per field
-    constexpr int kSfFields = kBlocks * C;
+    // Scale factors.  s == 4 (the default): a round's fields are kRoundSfBytes consecutive bytes; they are read as aligned 32-bit
+    // words one round ahead and realigned/byte-swapped by one PRMT (per-lane byte phase), so a round costs one global load
+    // instead of one byte load per field (the byte loads alone were 1.6 L1 tag requests per warp-sample).  Other s: byte pairs
+    // per field, one half ahead.
+    constexpr int kSfFields = Cfg::kBlk * C;                    // fields per half
+    constexpr int kRoundSfBytes = Cfg::kHalves * kSfFields / 2;  // at s == 4
+    static_assert(kRoundSfBytes == 4, "a round carries one 32-bit word of 4-bit scale factors");
+    const uint32_t *sfw = reinterpret_cast<const uint32_t *>(sea + (sf_off & ~(uint64_t)3));
+    const uint32_t sf_sel = 0x0123u + ((uint32_t)sf_off & 3u) * 0x1111u;
+    uint32_t sf_lo = 0, sf_hi = 0;  // aligned words r and r+1 of the section (s == 4)
     uint32_t sf_raw[kSfFields];
-    auto fetch_sf = [&](uint32_t r) {
+    auto fetch_sf = [&](uint32_t gh) {
 #pragma unroll
         for (int q = 0; q < kSfFields; q++) {
-            const uint32_t bit = (r * kSfFields + q) * s;
-            if (s == 4u) {
-                sf_raw[q] = __ldg(sfp + (bit >> 3));  // fields never straddle a byte
-            } else {
-                sf_raw[q] = ((uint32_t)__ldg(sfp + (bit >> 3)) << 8) | ((bit & 7u) + s > 8u ? (uint32_t)__ldg(sfp + (bit >> 3) + 1) : 0u);
-            }
+            const uint32_t bit = (gh * kSfFields + q) * s;
+            sf_raw[q] = ((uint32_t)__ldg(sfp + (bit >> 3)) << 8) | ((bit & 7u) + s > 8u ? (uint32_t)__ldg(sfp + (bit >> 3) + 1) : 0u);
         }
     };
     issue_round(0);
-    fetch_sf(0);
+    if (s == 4u) {
+        sf_lo = __ldg(sfw);
+        sf_hi = __ldg(sfw + 1);
+    } else {
+        fetch_sf(0);
+    }
+    const uint32_t n_halves = n_rounds * Cfg::kHalves;
 
     for (uint32_t r = 0; r < n_rounds; r++) {
         // my buffer (r+1)&1 was consumed in round r-1 (only I read my row): refill it, then wait for this round's slice
         if (r + 1 < n_rounds) issue_round(r + 1);
         else cp_async_commit();
         cp_async_wait1();
-        const uint32_t bo = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & 12u;  // word offset of the round inside its granule
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(in_rows + (r & 1u) * (Cfg::kRows * Cfg::kInPitch) + lane * Cfg::kInPitch + bo);
+        // byte offset of the round's first residual byte inside its staged row (the row starts at a 16-byte boundary of the file)
+        const uint32_t rb = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & 15u;
+        const uint32_t row_sh = my_in_sh + (r & 1u) * Cfg::kBufBytes;
 
-        // scale factors of this round's blocks (bytes fetched during the previous round), then prefetch the next round's
-        uint32_t sfv[kSfFields];
-#pragma unroll
-        for (int q = 0; q < kSfFields; q++) {
-            const uint32_t sh = ((r * kSfFields + q) * s) & 7u;
-            if (s == 4u) sfv[q] = (sf_raw[q] >> (4u - sh)) & 15u;
-            else sfv[q] = (sf_raw[q] >> (16u - sh - s)) & ((1u << s) - 1u);
+        uint32_t sf_round = 0;
+        if (s == 4u) {  // this round's 8 nibbles, big-endian; then prefetch the word the next round completes with
+            sf_round = __byte_perm(sf_lo, sf_hi, sf_sel);
+            sf_lo = sf_hi;
+            sf_hi = __ldg(sfw + r + 2);  // stays inside the chunk: the residual section follows
         }
-        if (r + 1 < n_rounds) fetch_sf(r + 1);
 
+        // The body below is ONE half (80 samples, every bit position a compile-time constant); it is looped, not unrolled
+        // further, so that the code (~24 KB) stays inside the 32 KB L1.5 instruction cache: with the round unrolled (56 KB) the
+        // top stall was "no instruction" (profiles/r01_decode_unrolled_lane_per_chunk_v7).
+#pragma unroll 1
+        for (uint32_t hh = 0; hh < (uint32_t)Cfg::kHalves; hh++) {
+            const uint32_t gh = r * Cfg::kHalves + hh;
+            // scale factors of this half's blocks
+            uint32_t sfv[kSfFields];
+            if (s == 4u) {
+                const uint32_t rw = sf_round >> (16u * (1u - hh));  // big-endian: the first half's four nibbles are the top 16 bits
 #pragma unroll
-        for (int hh = 0; hh < Cfg::kHalves; hh++) {
-            // window of this half: big-endian words W[0..], frame fi / channel c sits at bit (hh*kHB - 32*wlo) + (fi*C + c)*B
-            constexpr int kHB = Cfg::kHalfBits;
-            const int wlo = (hh * kHB) >> 5;
+                for (int q = 0; q < kSfFields; q++) sfv[q] = (rw >> (12 - 4 * q)) & 15u;
+            } else {
+#pragma unroll
+                for (int q = 0; q < kSfFields; q++) {
+                    const uint32_t sh = ((gh * kSfFields + q) * s) & 7u;
+                    sfv[q] = (sf_raw[q] >> (16u - sh - s)) & ((1u << s) - 1u);
+                }
+                if (gh + 1 < n_halves) fetch_sf(gh + 1);
+            }
+
+            // window of this half: big-endian words W[0..kNW), frame fi / channel c sits at bit (fi*C + c)*B.  The half starts at
+            // byte ob of the row: aligned words are loaded and the byte phase is undone by the PRMT that also swaps to big-endian.
             constexpr int kNW = Cfg::kNW;
+            const uint32_t ob = rb + hh * Cfg::kHalfBytes;
+            const uint32_t wsh = row_sh + (ob & ~3u);
+            const uint32_t prmt_sel = 0x0123u + (ob & 3u) * 0x1111u;
             uint32_t V[kNW + 1], W[kNW];
 #pragma unroll
-            for (int t = 0; t < kNW + 1; t++) V[t] = words[wlo + t];
+            for (int t = 0; t < kNW + 1; t++) V[t] = (uint32_t)lds_s32(wsh + 4 * t);
 #pragma unroll
             for (int t = 0; t < kNW; t++) W[t] = __byte_perm(V[t], V[t + 1], prmt_sel);
 
+            uint8_t *oh = out + (size_t)gh * (Cfg::HF * C * 2);
             uint32_t ow[8];  // 32 bytes of interleaved PCM being assembled
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
+            for (int q = 0; q < Cfg::kBlk; q++) {
                 uint32_t rowbase[C];
 #pragma unroll
-                for (int c = 0; c < C; c++) rowbase[c] = lut_sh + (sfv[(hh * 2 + q) * C + c] << (B + kShift));
+                for (int c = 0; c < C; c++) rowbase[c] = lut_sh + (sfv[q * C + c] << (B + kShift));
 #pragma unroll
                 for (int i = 0; i < Cfg::F; i++) {
                     const int fi = q * Cfg::F + i;  // frame inside the half
                     int32_t y[C];
 #pragma unroll
                     for (int c = 0; c < C; c++) {
-                        const int bit = (hh * kHB) - (wlo << 5) + (fi * C + c) * B;  // compile-time position of the field in W[]
+                        const int bit = (fi * C + c) * B;  // compile-time position of the field in W[]
                         const int wd = bit >> 5, off = bit & 31;
                         uint32_t x;
                         if (off + B <= 32) {
@@ -223,11 +271,16 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
                         } else {
                             x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - B - kShift) & 31);
                         }
-                        const int32_t d = lds_s32((x & (((1u << B) - 1u) << kShift)) | rowbase[c]);
+                        int32_t d, delta;
+                        if (kPair) {
+                            lds_s32x2((x & (((1u << B) - 1u) << kShift)) | rowbase[c], d, delta);
+                        } else {
+                            d = lds_s32((x & (((1u << B) - 1u) << kShift)) | rowbase[c]);
+                            delta = d >> 4;
+                        }
                         const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                              (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                         y[c] = clamp_i16((int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d));
-                        const int32_t delta = d >> 4;
                         w[c][0] += delta * sg[c][0];
                         w[c][1] += delta * sg[c][1];
                         w[c][2] += delta * sg[c][2];
@@ -236,15 +289,13 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
                         sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = (y[c] >> 31) | 1;
                     }
                     // interleaved i16 PCM: 8 stereo frames or 16 mono frames fill one 32-byte (full sector) store
-                    const int fa = hh * Cfg::HF + fi;  // frame inside the round
                     if (C == 2) {
-                        ow[fa & 7] = __byte_perm((uint32_t)y[0], (uint32_t)y[C - 1], 0x5410);
+                        ow[fi & 7] = __byte_perm((uint32_t)y[0], (uint32_t)y[C - 1], 0x5410);
                     } else {
-                        if ((fa & 1) == 0) ow[(fa >> 1) & 7] = (uint32_t)y[0] & 0xffffu;
-                        else ow[(fa >> 1) & 7] = __byte_perm(ow[(fa >> 1) & 7], (uint32_t)y[0], 0x5410);
+                        if ((fi & 1) == 0) ow[(fi >> 1) & 7] = (uint32_t)y[0] & 0xffffu;
+                        else ow[(fi >> 1) & 7] = __byte_perm(ow[(fi >> 1) & 7], (uint32_t)y[0], 0x5410);
                     }
-                    if ((fa % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid)
-                        st_global_256(out + ((size_t)r * (Cfg::RF / Cfg::kOutFrames) + fa / Cfg::kOutFrames) * 32, ow);
+                    if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256(oh + (fi / Cfg::kOutFrames) * 32, ow);
                 }
             }
         }
@@ -258,7 +309,7 @@ static bool plan_unrolled(uint32_t s, bool *repl, uint32_t *lut_align, size_t *s
     using Cfg = UCfg<C, B>;
     const uint32_t entries = 1u << (s + B);
     *repl = entries * 128u <= 16384u;
-    const uint32_t lut_bytes = *repl ? entries * 128u : entries * 4u;
+    const uint32_t lut_bytes = (*repl ? entries * 128u : entries * 4u) << SEA_DEC_PAIR;
     *lut_align = lut_bytes < 1024u ? 1024u : lut_bytes;  // power of two >= the table size
     *smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + *lut_align + lut_bytes;
     return Cfg::kWarps >= 8 && *smem <= 227u * 1024u;
@@ -312,7 +363,7 @@ bool decode_unrolled_supported(const DecFastParams &p)
     if (p.channels != 1 && p.channels != 2) return false;
     if ((p.hdr_word & 0xffu) != 1u) return false;  // CBR only
     if (p.F != 20 || p.b < 1 || p.b > 8 || p.s < 1 || p.s > 8) return false;
-    const uint32_t rf = ((p.channels * p.b) % 2 == 0) ? 80u : 160u;
+    const uint32_t rf = 160u / p.channels;  // frames per staged round (UCfg::RF)
     if (p.N % rf != 0 || p.N == 0) return false;
     return p.channels == 1 ? plan_unrolled_b<1>(p.b, p.s) : plan_unrolled_b<2>(p.b, p.s);
 }
