@@ -412,7 +412,11 @@ int sea_b200_ctx_create(int device, sea_b200_ctx **out)
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->own_stream = true;
-    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    {   // highest priority: its few long-running CTAs must be placed as soon as an SM frees up, not after the big grid drains
+        int prio_lo = 0, prio_hi = 0;
+        if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return bail(e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail(e);
+    }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);

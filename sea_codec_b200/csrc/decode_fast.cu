@@ -182,7 +182,7 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     static_assert(kRoundSfBytes == 4, "a round carries one 32-bit word of 4-bit scale factors");
     const uint32_t *sfw = reinterpret_cast<const uint32_t *>(sea + (sf_off & ~(uint64_t)3));
     const uint32_t sf_sel = 0x0123u + ((uint32_t)sf_off & 3u) * 0x1111u;
-    uint32_t sf_lo = 0, sf_hi = 0;  // aligned words r and r+1 of the section (s == 4)
+    uint32_t sf_lo = 0, sf_hi = 0, sf_new = 0;  // aligned words r, r+1 and (in flight) r+2 of the section (s == 4)
     uint32_t sf_raw[kSfFields];
     auto fetch_sf = [&](uint32_t gh) {
 #pragma unroll
@@ -212,8 +212,9 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
         uint32_t sf_round = 0;
         if (s == 4u) {  // this round's 8 nibbles, big-endian; then prefetch the word the next round completes with
             sf_round = __byte_perm(sf_lo, sf_hi, sf_sel);
-            sf_lo = sf_hi;
-            sf_hi = __ldg(sfw + r + 2);  // stays inside the chunk: the residual section follows
+            // stays inside the chunk (the residual section follows); rotated into sf_hi at the END of the round so that nothing
+            // waits for it here
+            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_new) : "l"(sfw + r + 2));
         }
 
         // The body below is ONE half (80 samples, every bit position a compile-time constant); it is looped, not unrolled
@@ -299,6 +300,8 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
                 }
             }
         }
+        sf_lo = sf_hi;
+        sf_hi = sf_new;
     }
 }
 

@@ -1,4 +1,4 @@
-"""Small decode-only workload for profiling / tuning: python tools/dec_probe.py [streams] [seconds] [bits] [channels] [iters]
+"""Small decode-only workload for profiling / tuning: python tools/dec_probe.py [streams] [seconds] [bits] [channels] [iters] [frames]
 Honours SEA_B200_LIB (tuning builds from tools/build_variant.py)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +13,7 @@ ch = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 dev = torch.device("cuda:0")
 ctx = S.Context(0)
-frames = secs * 44100
+frames = int(sys.argv[6]) if len(sys.argv) > 6 else secs * 44100  # argv[6]: exact frame count (e.g. a multiple of 5120: no partial chunk)
 st = S.EncoderSettings(residual_bits=bits)
 u = min(n, 16)
 pcm = synth.gen_batch_torch(u, frames, ch, 44100, dev)
