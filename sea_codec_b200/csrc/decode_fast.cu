@@ -24,9 +24,6 @@
 #ifndef SEA_DEC_WARPS
 #define SEA_DEC_WARPS 16
 #endif
-#ifndef SEA_DEC_PAIR
-#define SEA_DEC_PAIR 0  // 1: the look-up table holds (d, d >> 4) pairs read with one 64-bit load (saves the shift per sample)
-#endif
 
 namespace sea {
 
@@ -51,11 +48,6 @@ __device__ __forceinline__ int32_t lds_s32(uint32_t addr)
     int32_t v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
-}
-
-__device__ __forceinline__ void lds_s32x2(uint32_t addr, int32_t &a, int32_t &b)
-{
-    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
 }
 
 __device__ __forceinline__ uint32_t find_stream_f(const DecStream *streams, uint32_t n_streams, uint64_t chain)
@@ -95,41 +87,63 @@ struct UCfg {
 
 }  // namespace
 
-template <int C, int B, bool REPL>
+// MODE: how the dequantised residual of a code is looked up.
+//   kLutPlain     lut1[sf][code], 4-byte stride; one shift + one LOP3 per sample.
+//   kLutPair      two adjacent fields (the two channels of a frame, or two consecutive mono frames) are positioned by ONE shift:
+//                 the second field indexes lut1 (code stride 2^kShift), the first one, B bits higher, indexes lut0 whose code
+//                 stride is 2^(kShift+B); the scale-factor rows of lut0 are interleaved into the gaps, so it is no larger.
+//   kLutPairRepl  the same with every entry replicated per bank (stride 128 B, lane l at +4l): conflict-free dependent loads.
+enum : int { kLutPlain = 0, kLutPair = 1, kLutPairRepl = 2 };
+
+__host__ __device__ constexpr uint32_t lut_shift(int mode) { return mode == kLutPairRepl ? 7u : 2u; }
+__host__ __device__ inline uint32_t lut1_bytes(int mode, uint32_t s, uint32_t b) { return 1u << (s + b + lut_shift(mode)); }
+__host__ __device__ inline uint32_t lut0_bytes(int mode, uint32_t s, uint32_t b)
+{
+    return mode == kLutPlain ? 0u : 1u << (lut_shift(mode) + b + (b > s ? b : s));
+}
+// offset of row sf inside lut0 (code offset and lane offset are added by the caller)
+__host__ __device__ inline uint32_t lut0_row(int mode, uint32_t s, uint32_t b, uint32_t sf)
+{
+    const uint32_t sh = lut_shift(mode);
+    return s <= b ? sf << sh : ((sf & ((1u << b) - 1u)) << sh) + ((sf >> b) << (sh + 2u * b));
+}
+
+template <int C, int B, int MODE>
 __global__ void __launch_bounds__(UCfg<C, B>::kWarps * 32, 1)
 decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams,
-                       DecFastParams p, const int32_t *__restrict__ tab, uint32_t lut_align, int *err)
+                       DecFastParams p, const int32_t *__restrict__ tab, int *err)
 {
     using Cfg = UCfg<C, B>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s = p.s;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
-    // ---- dequant rows of residual size B: lut[sf][code], replicated per bank when REPL (entry stride 128 B, lane l at +4l).
-    // The table sits after the warp tiles at an address aligned to its own size, so "row base | code offset" never carries.
-    constexpr int kPair = SEA_DEC_PAIR;
-    constexpr int kShift = (REPL ? 7 : 2) + kPair;  // log2 of the byte stride between consecutive codes
+    // ---- dequant rows of residual size B.  Each table sits after the warp tiles at an address aligned to its own size (a power
+    // of two), so "row base | code offset" never carries.
+    constexpr int kShift = (int)lut_shift(MODE);  // log2 of the byte stride between consecutive codes of lut1
+    constexpr bool kPair = MODE != kLutPlain;
+    constexpr bool kRepl = MODE == kLutPairRepl;
     const uint32_t smem_sh = smem_u32(smem);
-    const uint32_t lut_abs = (smem_sh + Cfg::kWarps * Cfg::kWarpBytes + lut_align - 1u) & ~(lut_align - 1u);
-    int32_t *lut = reinterpret_cast<int32_t *>(smem + (lut_abs - smem_sh));
+    const uint32_t l0b = lut0_bytes(MODE, s, B), l1b = lut1_bytes(MODE, s, B);
+    const uint32_t a0 = l0b < 1024u ? 1024u : l0b, a1 = l1b < 1024u ? 1024u : l1b;
+    const uint32_t lut0_abs = (smem_sh + Cfg::kWarps * Cfg::kWarpBytes + a0 - 1u) & ~(a0 - 1u);
+    const uint32_t lut1_abs = (lut0_abs + l0b + a1 - 1u) & ~(a1 - 1u);
     {
+        int32_t *lut0 = reinterpret_cast<int32_t *>(smem + (lut0_abs - smem_sh));
+        int32_t *lut1 = reinterpret_cast<int32_t *>(smem + (lut1_abs - smem_sh));
         const uint32_t entries = 1u << (s + B);
         const int32_t *src = tab + tab_dqt_off(s, B);
-        if (kPair) {
-            const uint32_t n = REPL ? entries * 32u : entries;
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const int32_t d = src[REPL ? (i >> 5) : i];
-                lut[2 * i] = d;
-                lut[2 * i + 1] = d >> 4;  // lms.rs:44
-            }
-        } else if (REPL) {
-            for (uint32_t i = threadIdx.x; i < entries * 32u; i += blockDim.x) lut[i] = src[i >> 5];
-        } else {
-            for (uint32_t i = threadIdx.x; i < entries; i += blockDim.x) lut[i] = src[i];
+        const uint32_t reps = kRepl ? 32u : 1u;
+        for (uint32_t i = threadIdx.x; i < entries * reps; i += blockDim.x) {
+            const uint32_t e = kRepl ? i >> 5 : i, l = kRepl ? i & 31u : 0u;
+            const int32_t v = src[e];
+            lut1[(e << (kShift - 2)) + l] = v;
+            if (kPair) lut0[(lut0_row(MODE, s, B, e >> B) >> 2) + ((e & ((1u << B) - 1u)) << (kShift + B - 2)) + l] = v;
         }
     }
     __syncthreads();
-    const uint32_t lut_sh = lut_abs + (REPL ? (lane * 4u) << kPair : 0u);
+    const uint32_t lut_sh = lut1_abs + (kRepl ? lane * 4u : 0u);
+    const uint32_t lut0_sh = lut0_abs + (kRepl ? lane * 4u : 0u);
 
     uint8_t *in_rows = smem + warp * Cfg::kWarpBytes;  // [2][32 rows][kInPitch]
 
@@ -252,49 +266,75 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
 
             uint8_t *oh = out + (size_t)gh * (Cfg::HF * C * 2);
             uint32_t ow[8];  // 32 bytes of interleaved PCM being assembled
+            int32_t y_even = 0;  // mono: the clamped even frame waiting to be packed with the odd one
+            uint32_t xg = 0;  // the field group (one or two codes) last moved into look-up position
 #pragma unroll
             for (int q = 0; q < Cfg::kBlk; q++) {
-                uint32_t rowbase[C];
+                uint32_t rowbase[C], rowbase0[C];
 #pragma unroll
-                for (int c = 0; c < C; c++) rowbase[c] = lut_sh + (sfv[q * C + c] << (B + kShift));
+                for (int c = 0; c < C; c++) {
+                    rowbase[c] = lut_sh + (sfv[q * C + c] << (B + kShift));
+                    rowbase0[c] = kPair ? lut0_sh + lut0_row(MODE, s, B, sfv[q * C + c]) : 0u;
+                }
 #pragma unroll
                 for (int i = 0; i < Cfg::F; i++) {
                     const int fi = q * Cfg::F + i;  // frame inside the half
-                    int32_t y[C];
+                    int32_t y[C], d[C];
 #pragma unroll
                     for (int c = 0; c < C; c++) {
-                        const int bit = (fi * C + c) * B;  // compile-time position of the field in W[]
-                        const int wd = bit >> 5, off = bit & 31;
-                        uint32_t x;
-                        if (off + B <= 32) {
-                            const int rs = 32 - off - B - kShift;
-                            x = rs >= 0 ? (W[wd] >> (rs & 31)) : (W[wd] << ((-rs) & 31));
-                        } else {
-                            x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - B - kShift) & 31);
+                        const int n = fi * C + c;            // sample inside the half
+                        const int pb = kPair ? (n & ~1) : n;  // first sample of the group positioned by one shift
+                        constexpr int kGB = kPair ? 2 * B : B;
+                        if (n == pb) {
+                            const int bit = pb * B;  // compile-time position of the group in W[]
+                            const int wd = bit >> 5, off = bit & 31;
+                            if (off + kGB <= 32) {
+                                const int rs = 32 - off - kGB - kShift;
+                                xg = rs >= 0 ? (W[wd] >> (rs & 31)) : (W[wd] << ((-rs) & 31));
+                            } else {
+                                xg = __funnelshift_r(W[wd + 1], W[wd], (64 - off - kGB - kShift) & 31);
+                            }
                         }
-                        int32_t d, delta;
-                        if (kPair) {
-                            lds_s32x2((x & (((1u << B) - 1u) << kShift)) | rowbase[c], d, delta);
-                        } else {
-                            d = lds_s32((x & (((1u << B) - 1u) << kShift)) | rowbase[c]);
-                            delta = d >> 4;
-                        }
+                        uint32_t addr;
+                        if (kPair && n == pb) addr = (xg & (((1u << B) - 1u) << (kShift + B))) | rowbase0[c];
+                        else addr = (xg & (((1u << B) - 1u) << kShift)) | rowbase[c];
+                        d[c] = lds_s32(addr);
                         const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                              (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
-                        y[c] = clamp_i16((int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d));
+                        y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:38, before the clamp
+                    }
+                    // clamp_i16 (common.rs:5-8).  Stereo: one I2IP saturates both channels and packs them into the output word
+                    // (2 issue slots fewer per frame than 4 VIMNMX + PRMT); the clamped values are unpacked for the history.
+                    uint32_t packed = 0;
+                    int32_t sgn[C];  // the clamp keeps the sign: take it from the unclamped sum (off the I2IP -> unpack path)
+#pragma unroll
+                    for (int c = 0; c < C; c++) sgn[c] = (y[c] >> 31) | 1;
+                    if (C == 2) {
+                        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[C - 1]), "r"(y[0]));
+                        y[0] = (int32_t)(int16_t)(packed & 0xffffu);
+                        y[C - 1] = (int32_t)packed >> 16;
+                    } else if ((fi & 1) == 0) {
+                        y[0] = clamp_i16(y[0]);
+                        y_even = y[0];
+                    } else {  // mono: the odd frame is saturated while it is packed next to the even one
+                        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[0]), "r"(y_even));
+                        y[0] = (int32_t)packed >> 16;
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const int32_t delta = d[c] >> 4;
                         w[c][0] += delta * sg[c][0];
                         w[c][1] += delta * sg[c][1];
                         w[c][2] += delta * sg[c][2];
                         w[c][3] += delta * sg[c][3];
                         h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
-                        sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = (y[c] >> 31) | 1;
+                        sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
                     }
                     // interleaved i16 PCM: 8 stereo frames or 16 mono frames fill one 32-byte (full sector) store
                     if (C == 2) {
-                        ow[fi & 7] = __byte_perm((uint32_t)y[0], (uint32_t)y[C - 1], 0x5410);
+                        ow[fi & 7] = packed;
                     } else {
-                        if ((fi & 1) == 0) ow[(fi >> 1) & 7] = (uint32_t)y[0] & 0xffffu;
-                        else ow[(fi >> 1) & 7] = __byte_perm(ow[(fi >> 1) & 7], (uint32_t)y[0], 0x5410);
+                        if (fi & 1) ow[(fi >> 1) & 7] = packed;
                     }
                     if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256(oh + (fi / Cfg::kOutFrames) * 32, ow);
                 }
@@ -305,58 +345,61 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     }
 }
 
-// Shared-memory plan of decode_unrolled_kernel<C, B> for scale_factor_bits s: replicated table when it is <= 16 KB.
+// Shared-memory plan of decode_unrolled_kernel<C, B> for scale_factor_bits s: the look-up mode and the dynamic shared memory.
 template <int C, int B>
-static bool plan_unrolled(uint32_t s, bool *repl, uint32_t *lut_align, size_t *smem)
+static bool plan_unrolled(uint32_t s, int *mode, size_t *smem)
 {
     using Cfg = UCfg<C, B>;
-    const uint32_t entries = 1u << (s + B);
-    *repl = entries * 128u <= 16384u;
-    const uint32_t lut_bytes = (*repl ? entries * 128u : entries * 4u) << SEA_DEC_PAIR;
-    *lut_align = lut_bytes < 1024u ? 1024u : lut_bytes;  // power of two >= the table size
-    *smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + *lut_align + lut_bytes;
+    const uint32_t hi = B > s ? B : s;
+    // Pairing without replication was measured and dropped: lut0's bank is then a function of the scale factor alone
+    // (code stride 2^(2+B) bytes), and the conflicts cost more than the saved shift (B = 5: 7.3 ms against 4.9 ms plain).
+    if (s + B <= 7 && B + hi <= 8) *mode = kLutPairRepl;   // both tables <= 32 KB with 128-byte entries
+    else *mode = kLutPlain;
+    const uint32_t l0 = lut0_bytes(*mode, s, B), l1 = lut1_bytes(*mode, s, B);
+    *smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + (l0 ? (l0 < 1024u ? 1024u : l0) + l0 : 0u) + (l1 < 1024u ? 1024u : l1) + l1;
     return Cfg::kWarps >= 8 && *smem <= 227u * 1024u;
+}
+
+template <int C, int B, int MODE>
+static cudaError_t launch_unrolled_mode(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
+                                        const int32_t *tab, int *d_err, size_t smem, cudaStream_t stream)
+{
+    using Cfg = UCfg<C, B>;
+    const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
+    const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
+    cudaError_t e = cudaFuncSetAttribute(decode_unrolled_kernel<C, B, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    decode_unrolled_kernel<C, B, MODE><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    return cudaGetLastError();
 }
 
 template <int C, int B>
 static cudaError_t launch_unrolled(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
                                    const int32_t *tab, int *d_err, cudaStream_t stream)
 {
-    using Cfg = UCfg<C, B>;
-    bool repl;
-    uint32_t lut_align;
+    int mode;
     size_t smem;
-    if (!plan_unrolled<C, B>(p.s, &repl, &lut_align, &smem)) return cudaErrorInvalidConfiguration;
-    const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
-    const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
-    cudaError_t e;
-    if (repl) {
-        e = cudaFuncSetAttribute(decode_unrolled_kernel<C, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        decode_unrolled_kernel<C, B, true><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, lut_align, d_err);
-    } else {
-        e = cudaFuncSetAttribute(decode_unrolled_kernel<C, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        decode_unrolled_kernel<C, B, false><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, lut_align, d_err);
+    if (!plan_unrolled<C, B>(p.s, &mode, &smem)) return cudaErrorInvalidConfiguration;
+    switch (mode) {
+        case kLutPairRepl: return launch_unrolled_mode<C, B, kLutPairRepl>(d_sea, d_pcm, d_streams, p, tab, d_err, smem, stream);
+        default: return launch_unrolled_mode<C, B, kLutPlain>(d_sea, d_pcm, d_streams, p, tab, d_err, smem, stream);
     }
-    return cudaGetLastError();
 }
 
 template <int C>
 static bool plan_unrolled_b(uint32_t b, uint32_t s)
 {
-    bool repl;
-    uint32_t la;
+    int mode;
     size_t smem;
     switch (b) {
-        case 1: return plan_unrolled<C, 1>(s, &repl, &la, &smem);
-        case 2: return plan_unrolled<C, 2>(s, &repl, &la, &smem);
-        case 3: return plan_unrolled<C, 3>(s, &repl, &la, &smem);
-        case 4: return plan_unrolled<C, 4>(s, &repl, &la, &smem);
-        case 5: return plan_unrolled<C, 5>(s, &repl, &la, &smem);
-        case 6: return plan_unrolled<C, 6>(s, &repl, &la, &smem);
-        case 7: return plan_unrolled<C, 7>(s, &repl, &la, &smem);
-        case 8: return plan_unrolled<C, 8>(s, &repl, &la, &smem);
+        case 1: return plan_unrolled<C, 1>(s, &mode, &smem);
+        case 2: return plan_unrolled<C, 2>(s, &mode, &smem);
+        case 3: return plan_unrolled<C, 3>(s, &mode, &smem);
+        case 4: return plan_unrolled<C, 4>(s, &mode, &smem);
+        case 5: return plan_unrolled<C, 5>(s, &mode, &smem);
+        case 6: return plan_unrolled<C, 6>(s, &mode, &smem);
+        case 7: return plan_unrolled<C, 7>(s, &mode, &smem);
+        case 8: return plan_unrolled<C, 8>(s, &mode, &smem);
         default: return false;
     }
 }
