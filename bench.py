@@ -41,6 +41,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(streams: int, seconds: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per launch, from the committed `ncu --set full` capture
+    (profiles/r01_decode_traffic.json: bytes per stream of the 60 s config-4 shape); None when the shape differs."""
+    p = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
+    try:
+        t = json.load(open(p))
+        if seconds != t["seconds"]:
+            return None
+        return float(t["dram_bytes_per_launch"]) / t["streams"] * streams
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -52,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -180,8 +193,8 @@ def workload_config(args, unique):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)  # ~0.6 s timed region: enough nvidia-smi clock samples
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="decode streams per GPU (config 4)")
     ap.add_argument("--enc-streams", type=int, default=1024, help="encode streams per GPU (config 5)")
@@ -277,8 +290,10 @@ def main():
     peaks, peak_src = measured_peaks()
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "decode_staged_kernel<2,3>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "decode_unrolled_kernel<2,3,pair-repl> (+ decode_staged_kernel<2,0> for the partial last chunks, "
+                                          "side stream)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(n, args.seconds), "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_msamples_per_s": samples_per_step / (k_ms * 1e-3) / 1e6}
 

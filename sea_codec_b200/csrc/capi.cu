@@ -56,6 +56,14 @@ struct sea_b200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side = nullptr;                       // partial-chunk decode runs beside the full-chunk kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // second decode lane: sea_b200_decode_batch pipelines groups of streams (H2D of group i+1 and D2H of group i-1 overlap the
+    // kernels of group i), alternating between the primary resources above and these
+    struct {
+        cudaStream_t stream = nullptr, side = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev0 = nullptr, ev1 = nullptr;
+        DevBuf in, out, table;
+        int *d_err = nullptr;
+    } aux;
     std::string last_error;
     uint64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -165,8 +173,23 @@ int plan_decode(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *headers, s
     return SEA_B200_OK;
 }
 
+// The resources one decode launch sequence uses: lane 0 = the context's own stream and buffers, lane 1 = the auxiliary set.
+struct DecLane {
+    cudaStream_t stream, side;
+    cudaEvent_t ev_fork, ev_join, ev0, ev1;
+    DevBuf *in, *out, *table;
+    int *d_err;
+    double kernel_ms;
+};
+DecLane decode_lane(sea_b200_ctx *ctx, int i)
+{
+    if (i == 0) return {ctx->stream, ctx->side, ctx->ev_fork, ctx->ev_join, ctx->ev0, ctx->ev1, &ctx->in, &ctx->out, &ctx->streams, ctx->d_err, 0.0};
+    return {ctx->aux.stream, ctx->aux.side, ctx->aux.ev_fork, ctx->aux.ev_join, ctx->aux.ev0, ctx->aux.ev1, &ctx->aux.in, &ctx->aux.out,
+            &ctx->aux.table, ctx->aux.d_err, 0.0};
+}
+
 // d_sea / d_pcm are device pointers; first_hdr_word = first 4 bytes of the first chunk of stream 0 (host copy).
-int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t sea_len, int16_t *d_pcm, bool have_hdr_word,
+int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_sea, uint64_t sea_len, int16_t *d_pcm, bool have_hdr_word,
                uint32_t hdr_word)
 {
     const uint32_t n_streams = (uint32_t)job.streams.size();
@@ -216,12 +239,12 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
         }
         if (chains_a == 0) unrolled = false;
     }
-    CU(ctx->streams.reserve(sizeof(DecStream) * table.size()));
-    CU(cudaMemcpyAsync(ctx->streams.p, table.data(), sizeof(DecStream) * table.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-    const DecStream *d_all = ctx->streams.as<DecStream>();
+    CU(L.table->reserve(sizeof(DecStream) * table.size()));
+    CU(cudaMemcpyAsync(L.table->p, table.data(), sizeof(DecStream) * table.size(), cudaMemcpyHostToDevice, L.stream));
+    CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
+    const DecStream *d_all = L.table->as<DecStream>();
 
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaEventRecord(L.ev0, L.stream));
     int dev_err = 0;
     if (fast) {
         if (unrolled) {
@@ -231,35 +254,36 @@ int run_decode(sea_b200_ctx *ctx, DecodeJob &job, const uint8_t *d_sea, uint64_t
             // The left-over chunks (one partial chunk per stream: a short grid of long serial chains) go first, on the side
             // stream, so that their latency hides under the full-chunk kernel instead of trailing it.
             if (fb.total_chunks) {
-                CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-                CU(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-                CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, ctx->d_err, ctx->side));
+                CU(cudaEventRecord(L.ev_fork, L.stream));
+                CU(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
+                CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, L.d_err, L.side));
                 ctx->launches++;
-                CU(cudaEventRecord(ctx->ev_join, ctx->side));
+                CU(cudaEventRecord(L.ev_join, L.side));
             }
-            CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, ctx->d_err, ctx->stream));
+            CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
             ctx->launches++;
-            if (fb.total_chunks) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+            if (fb.total_chunks) CU(cudaStreamWaitEvent(L.stream, L.ev_join, 0));
         } else {
-            CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all, fp, ctx->tabs, ctx->d_err, ctx->stream));
+            CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all, fp, ctx->tabs, L.d_err, L.stream));
             ctx->launches++;
         }
-        CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(&dev_err, L.d_err, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+        CU(cudaStreamSynchronize(L.stream));
         if (dev_err != kDevOk) {  // some chunk is not what the fast path was specialised for: redo everything generically
             fast = false;
-            CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+            CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
         }
     }
     if (!fast) {
-        CU(launch_decode_generic(d_sea, d_pcm, d_all, n_streams, job.total_chains, ctx->tabs, ctx->d_err, ctx->stream));
+        CU(launch_decode_generic(d_sea, d_pcm, d_all, n_streams, job.total_chains, ctx->tabs, L.d_err, L.stream));
         ctx->launches++;
-        CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&dev_err, L.d_err, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
     }
-    CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(L.ev1, L.stream));
+    CU(cudaStreamSynchronize(L.stream));
     float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ms, L.ev0, L.ev1);
+    L.kernel_ms = ms;
     ctx->last_kernel_ms = ms;
     return map_dev_error(ctx, dev_err);
 }
@@ -419,6 +443,17 @@ int sea_b200_ctx_create(int device, sea_b200_ctx **out)
     }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    {   // auxiliary decode lane
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithFlags(&ctx->aux.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->aux.side, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->aux.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->aux.ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreate(&ctx->aux.ev0)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreate(&ctx->aux.ev1)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&ctx->aux.d_err, sizeof(int))) != cudaSuccess) return bail(e);
+    }
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(e);
@@ -450,6 +485,16 @@ void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
     ctx->misc.release();
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->d_ties) cudaFree(ctx->d_ties);
+    if (ctx->aux.stream) { cudaStreamSynchronize(ctx->aux.stream); cudaStreamDestroy(ctx->aux.stream); }
+    if (ctx->aux.side) { cudaStreamSynchronize(ctx->aux.side); cudaStreamDestroy(ctx->aux.side); }
+    if (ctx->aux.ev_fork) cudaEventDestroy(ctx->aux.ev_fork);
+    if (ctx->aux.ev_join) cudaEventDestroy(ctx->aux.ev_join);
+    if (ctx->aux.ev0) cudaEventDestroy(ctx->aux.ev0);
+    if (ctx->aux.ev1) cudaEventDestroy(ctx->aux.ev1);
+    if (ctx->aux.d_err) cudaFree(ctx->aux.d_err);
+    ctx->aux.in.release();
+    ctx->aux.out.release();
+    ctx->aux.table.release();
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -567,7 +612,8 @@ int sea_b200_decode_batch_device(sea_b200_ctx *ctx, uint32_t n_streams, const ui
         hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
         have = true;
     }
-    rc = run_decode(ctx, job, d_sea, sea_len, d_pcm, have, hdr_word);
+    DecLane L = decode_lane(ctx, 0);
+    rc = run_decode(ctx, L, job, d_sea, sea_len, d_pcm, have, hdr_word);
     if (n_samples)
         for (uint32_t i = 0; i < n_streams; i++) n_samples[i] = rc == SEA_B200_OK ? job.n_samples[i] : 0;
     if (rc == SEA_B200_OK && job.trailing_invalid_frame)
@@ -603,23 +649,101 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
     }
     if (phi == 0) plo = 0;
     if (phi && !pcm) return SEA_B200_ERR_INVALID_PARAMETERS;
-    for (auto &d : job.streams) d.pcm_off -= plo;
     const uint64_t in_bytes = hi - lo, out_samples = phi - plo;
-    CU(ctx->in.reserve(in_bytes + 64));
-    CU(ctx->out.reserve(out_samples * 2 + 64));
-    CU(cudaMemcpyAsync(ctx->in.p, sea + lo, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    uint32_t hdr_word = 0;
-    bool have = false;
-    if (job.streams[0].n_chunks > 0 && job.streams[0].data_len >= 4) {
-        const uint8_t *w = sea + sea_offsets[0] + kFileHeaderBytes;
-        hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
-        have = true;
+
+    // ---- group the streams (index order) so that copies and kernels of neighbouring groups overlap: PCIe is the bound of this
+    // entry point (2 bytes out per sample against ~0.4 in), so the D2H engine should never wait for a kernel or an upload.
+    struct Group {
+        uint32_t i0, i1;
+        uint64_t lo, hi, plo, phi;  // byte range of the .sea input (relative to the batch range), sample range of the PCM output
+    };
+    std::vector<Group> groups;
+    {
+        const uint64_t target = 96ull << 20;  // PCM samples per group (192 MB): long enough to amortise launches, short enough to pipeline
+        Group g = {0, 0, UINT64_MAX, 0, UINT64_MAX, 0};
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < n_streams; i++) {
+            g.lo = std::min(g.lo, rel_off[i]);
+            g.hi = std::max(g.hi, rel_off[i] + sea_lens[i]);
+            if (job.n_samples[i]) {
+                g.plo = std::min(g.plo, pcm_offsets[i]);
+                g.phi = std::max(g.phi, pcm_offsets[i] + job.n_samples[i]);
+            }
+            acc += job.n_samples[i];
+            if (acc >= target || i + 1 == n_streams) {
+                g.i1 = i + 1;
+                if (g.phi == 0) g.plo = 0;
+                groups.push_back(g);
+                g = {i + 1, 0, UINT64_MAX, 0, UINT64_MAX, 0};
+                acc = 0;
+            }
+        }
+        uint64_t sum_in = 0, sum_out = 0;
+        for (const Group &q : groups) {
+            sum_in += q.hi - q.lo;
+            sum_out += q.phi - q.plo;
+        }
+        // scattered or interleaved layouts would make the per-group ranges overlap: ship the batch as one group then
+        if (groups.size() < 3 || sum_in > in_bytes + in_bytes / 4 + 4096 || sum_out > out_samples + out_samples / 4 + 4096)
+            groups.assign(1, Group{0, n_streams, 0, in_bytes, plo, phi});
     }
-    rc = run_decode(ctx, job, ctx->in.as<uint8_t>(), in_bytes, ctx->out.as<int16_t>(), have, hdr_word);
-    if (rc == SEA_B200_OK && out_samples) {
-        CU(cudaMemcpyAsync(pcm + plo, ctx->out.p, out_samples * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+    const bool piped = groups.size() > 1;
+    uint64_t max_in = 0, max_out = 0;
+    for (const Group &q : groups) {
+        max_in = std::max(max_in, q.hi - q.lo);
+        max_out = std::max(max_out, q.phi - q.plo);
     }
+    CU(ctx->in.reserve(max_in + 64));
+    CU(ctx->out.reserve(max_out * 2 + 64));
+    if (piped) {
+        CU(ctx->aux.in.reserve(max_in + 64));
+        CU(ctx->aux.out.reserve(max_out * 2 + 64));
+        CU(cudaEventRecord(ctx->aux.ev0, ctx->stream));  // order the auxiliary lane after whatever the caller queued before us
+        CU(cudaStreamWaitEvent(ctx->aux.stream, ctx->aux.ev0, 0));
+    }
+    auto upload = [&](size_t gi) -> cudaError_t {
+        const Group &q = groups[gi];
+        DecLane L = decode_lane(ctx, (int)(gi & 1));
+        return cudaMemcpyAsync(L.in->p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, L.stream);
+    };
+    double kernel_ms = 0.0;
+    CU(upload(0));
+    for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
+        const Group &q = groups[gi];
+        if (gi + 1 < groups.size()) CU(upload(gi + 1));  // queued behind the other lane's previous download, ahead of our kernels
+        DecLane L = decode_lane(ctx, (int)(gi & 1));
+        DecodeJob sub;
+        sub.streams.assign(job.streams.begin() + q.i0, job.streams.begin() + q.i1);
+        sub.n_samples.assign(job.n_samples.begin() + q.i0, job.n_samples.begin() + q.i1);
+        const uint32_t chain0 = sub.streams.empty() ? 0u : sub.streams[0].chain_begin;
+        for (auto &d : sub.streams) {
+            d.data_off -= q.lo;
+            d.pcm_off -= q.plo;
+            d.chain_begin -= chain0;
+        }
+        const DecStream &last = job.streams[q.i1 - 1];
+        sub.total_chains = (uint64_t)last.chain_begin + (uint64_t)last.n_chunks * last.channels - chain0;
+        // the group's own first stream decides its specialisation (a mixed batch may still have uniform groups)
+        if (parse_file_header(&headers[(size_t)q.i0 * kFileHeaderBytes], kFileHeaderBytes, &sub.first) != SEA_B200_OK) sub.first = job.first;
+        sub.uniform = true;
+        for (const DecStream &d : sub.streams)
+            if (d.channels != sub.first.channels || d.chunk_size != sub.first.chunk_size || d.frames_per_chunk != sub.first.frames_per_chunk)
+                sub.uniform = false;
+        uint32_t hdr_word = 0;
+        bool have = false;
+        if (!sub.streams.empty() && sub.streams[0].n_chunks > 0 && sub.streams[0].data_len >= 4) {
+            const uint8_t *w = sea + sea_offsets[q.i0] + kFileHeaderBytes;
+            hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
+            have = true;
+        }
+        rc = run_decode(ctx, L, sub, L.in->as<uint8_t>(), q.hi - q.lo, L.out->as<int16_t>(), have, hdr_word);
+        kernel_ms += L.kernel_ms;
+        if (rc == SEA_B200_OK && q.phi > q.plo)
+            CU(cudaMemcpyAsync(pcm + q.plo, L.out->p, (q.phi - q.plo) * 2, cudaMemcpyDeviceToHost, L.stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (piped) CU(cudaStreamSynchronize(ctx->aux.stream));
+    ctx->last_kernel_ms = kernel_ms;
     if (n_samples)
         for (uint32_t i = 0; i < n_streams; i++) n_samples[i] = rc == SEA_B200_OK ? job.n_samples[i] : 0;
     if (rc == SEA_B200_OK && job.trailing_invalid_frame)
@@ -858,7 +982,8 @@ int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, u
     CU(ctx->in.reserve(len + 64));
     CU(ctx->out.reserve(frames * h.channels * 2 + 64));
     CU(cudaMemcpyAsync(ctx->in.p, chunk, len, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = run_decode(ctx, job, ctx->in.as<uint8_t>(), len, ctx->out.as<int16_t>(), false, 0);
+    DecLane L = decode_lane(ctx, 0);
+    int rc = run_decode(ctx, L, job, ctx->in.as<uint8_t>(), len, ctx->out.as<int16_t>(), false, 0);
     if (rc) return rc;
     CU(cudaMemcpyAsync(pcm, ctx->out.p, frames * h.channels * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

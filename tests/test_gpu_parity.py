@@ -355,6 +355,40 @@ def test_device_resident_batch_and_properties(ctx, oracle):
     assert np.sqrt(np.mean((err / 32767.0) ** 2)) < 0.05
 
 
+def test_pipelined_host_buffer_decode(ctx, oracle):
+    """sea_b200_decode_batch with host buffers splits a large batch into groups and pipelines H2D / kernels / D2H over two
+    lanes (capi.cu).  Every group boundary and both lanes must give what the one-shot decode gives: four distinct streams
+    (one with a partial last chunk shared by all) against the oracle, 96 replicas against those."""
+    n_streams, frames, ch = 96, 5120 * 430 + 777, 2   # 96 x 4.4 M samples = 423 M samples -> 5 groups of <= 96 Mi samples
+    settings = S.EncoderSettings()
+    uniq = [synth.gen_stream(100 + i, frames, ch, 44100) for i in range(4)]
+    files = ctx.encode_batch(uniq, 44100, ch, settings)
+    for f, u in zip(files[:2], uniq[:2]):
+        assert f == oracle.sea_encode(u, 44100, ch, oracle.make_settings(3.0))
+    want = [ctx.sea_decode(f).samples for f in files]
+    assert np.array_equal(want[0], oracle.sea_decode(files[0]).samples)
+    flen = len(files[0])
+    stride = (flen + 15) // 16 * 16
+    sea = np.zeros(n_streams * stride, dtype=np.uint8)
+    for i in range(n_streams):
+        sea[i * stride: i * stride + flen] = np.frombuffer(files[i % 4], dtype=np.uint8)
+    spp = frames * ch
+    pcm = np.zeros(n_streams * spp, dtype=np.int16)
+    n = ctx.decode_batch_host(sea.ctypes.data, np.arange(n_streams) * stride, np.full(n_streams, flen), pcm.ctypes.data,
+                              np.arange(n_streams) * spp, np.full(n_streams, spp))
+    assert np.all(n == spp)
+    pcm = pcm.reshape(n_streams, spp)
+    for i in range(n_streams):
+        assert np.array_equal(pcm[i], want[i % 4]), f"stream {i} differs after the pipelined decode"
+    # scattered layout (streams in reverse order): the grouping must fall back to one range and still be right
+    order = np.arange(n_streams)[::-1].copy()
+    pcm2 = np.zeros(8 * spp, dtype=np.int16)
+    n2 = ctx.decode_batch_host(sea.ctypes.data, order[:8] * stride, np.full(8, flen), pcm2.ctypes.data, np.arange(8) * spp)
+    assert np.all(n2 == spp)
+    for j in range(8):
+        assert np.array_equal(pcm2.reshape(8, spp)[j], want[int(order[j]) % 4])
+
+
 def test_cpp_host_mirror(ctx, oracle, tmp_path):
     """include/sea_b200.hpp (the compiled-language host mirror of src/encoder.rs, src/decoder.rs, src/lib.rs) driven the way
     tests/streaming.rs drives the crate: one-shot encode, chunk-at-a-time SeaEncoder, SeaDecoder over the result."""
