@@ -18,6 +18,7 @@
 #ifndef SEA_B200_H
 #define SEA_B200_H
 
+#include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -166,6 +167,47 @@ int sea_b200_decoder_header(const sea_b200_decoder *dec, sea_b200_header *out);
 int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, uint64_t len, int64_t remaining_frames,
                                   int16_t *pcm, uint64_t pcm_cap_samples, uint64_t *n_samples);
 void sea_b200_decoder_destroy(sea_b200_decoder *dec);
+
+/* Multi-chunk forms of the two seam calls: the same state machine, several chunks per call (one launch, one H2D, one D2H).
+ * make_chunks: n_samples may span any number of chunks; the serialized chunks follow each other in `out` (all but the last
+ * are full chunks of sea_b200_encoder_chunk_size() bytes); *n_chunks receives their count.  The LMS state and
+ * prev_scalefactor stay on the device between calls (encoder_base.rs:181-182). */
+int sea_b200_encoder_make_chunks(sea_b200_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint8_t *out, uint64_t out_cap,
+                                 uint64_t *out_len, uint32_t *n_chunks);
+/* decode_chunks: `chunks` = consecutive chunks as they lie in the file (every one chunk_size bytes, the last may be the
+ * stream's short final chunk when remaining_frames >= 0); decoded chunk-parallel. */
+int sea_b200_decoder_decode_chunks(sea_b200_decoder *dec, sea_b200_ctx *ctx, const uint8_t *chunks, uint64_t len,
+                                   int64_t remaining_frames, int16_t *pcm, uint64_t pcm_cap_samples, uint64_t *n_samples);
+
+/* ---------------------------------------------------------------- random access (README.md:125 "seeking" future work) */
+
+/* Decodes frames [first_frame, first_frame + n_frames) of a complete .sea file: only the chunks that cover the range are
+ * shipped and decoded (chunk k starts at byte 22 + k*chunk_size, file.rs:185, and carries its own LMS state,
+ * chunk.rs:95-103).  The range is clamped to the file; pcm == NULL returns the sample count only.
+ * flags: SEA_B200_RANGE_SKIP_METADATA makes chunk data start after the header's metadata bytes -- the format-compatible fix
+ * of the reference decoder's metadata bug (file.rs:53-54 reads zero bytes); default 0 mirrors the reference. */
+#define SEA_B200_RANGE_SKIP_METADATA 1u
+int sea_b200_decode_range(sea_b200_ctx *ctx, const uint8_t *sea, uint64_t len, uint64_t first_frame, uint64_t n_frames,
+                          uint32_t flags, int16_t *pcm, uint64_t pcm_cap_samples, uint64_t *n_samples, uint32_t *sample_rate,
+                          uint32_t *channels);
+
+/* ---------------------------------------------------------------- the reference's existing foreign surfaces */
+
+/* src/wasm_api.rs:32-111 (wasm_sea_encode / wasm_sea_decode / allocate / deallocate / setup) with the same argument lists,
+ * served by a process-wide context on GPU $SEA_B200_DEVICE (default 0).  Where the reference asserts/panics these return 0
+ * and sea_b200_wasm_status() holds the SEA_B200_ERR_* code.  input_length / output_length are BYTES (wasm_api.rs:45,83). */
+void sea_b200_wasm_setup(void);
+size_t sea_b200_wasm_sea_encode(const int16_t *input_samples, size_t input_length, uint32_t sample_rate, uint32_t channels,
+                                float bitrate, bool vbr, uint8_t *output_buffer, size_t output_length);
+size_t sea_b200_wasm_sea_decode(const uint8_t *encoded, size_t encoded_length, int16_t *output_buffer, size_t output_length,
+                                uint32_t *sample_rate, uint32_t *channels);
+uint8_t *sea_b200_wasm_allocate(size_t size);             /* pinned host memory */
+void sea_b200_wasm_deallocate(uint8_t *ptr, size_t size);
+int sea_b200_wasm_status(void);
+/* c/sea.h:189 `int sea_decode(encoded, encoded_len, &sample_rate, &channels, output, &total_frames)`: same arguments, same
+ * return codes (0 ok, 1 invalid file, 2 decode error), same two-call pattern (output == NULL fills the header fields only). */
+int sea_b200_csea_decode(uint8_t *encoded, uint32_t encoded_len, uint32_t *sample_rate, uint32_t *channels, int16_t *output,
+                         uint32_t *total_frames);
 
 /* ---------------------------------------------------------------- measurement helpers */
 

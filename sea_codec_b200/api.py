@@ -131,6 +131,17 @@ SYMBOLS = {
     "sea_b200_decoder_header": (C.c_int, [C.c_void_p, C.POINTER(_Header)]),
     "sea_b200_decoder_decode_chunk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_uint64, _u64p]),
     "sea_b200_decoder_destroy": (None, [C.c_void_p]),
+    "sea_b200_encoder_make_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "sea_b200_decoder_decode_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_uint64, _u64p]),
+    "sea_b200_decode_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64,
+                                        _u64p, _u32p, _u32p]),
+    "sea_b200_wasm_setup": (None, []),
+    "sea_b200_wasm_sea_encode": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_float, C.c_bool, C.c_void_p, C.c_size_t]),
+    "sea_b200_wasm_sea_decode": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _u32p, _u32p]),
+    "sea_b200_wasm_allocate": (C.c_void_p, [C.c_size_t]),
+    "sea_b200_wasm_deallocate": (None, [C.c_void_p, C.c_size_t]),
+    "sea_b200_wasm_status": (C.c_int, []),
+    "sea_b200_csea_decode": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, _u32p]),
     "sea_b200_int32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sea_b200_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "sea_b200_last_vbr_ties": (C.c_uint64, [C.c_void_p]),
@@ -235,6 +246,18 @@ class Context:
         out = np.empty(max(int(n.value), 1), dtype=np.int16)
         self._check(self._L.sea_b200_decode(self._h, buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(n), C.byref(rate),
                                             C.byref(ch)))
+        return SeaDecodeInfo(out[: n.value], rate.value, ch.value)
+
+    def decode_range(self, encoded: bytes, first_frame: int, n_frames: int, skip_metadata: bool = False) -> SeaDecodeInfo:
+        """Random access: frames [first_frame, first_frame + n_frames) of a .sea file; only the covering chunks are decoded."""
+        buf = np.frombuffer(encoded, dtype=np.uint8)
+        n, rate, ch = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        flags = 1 if skip_metadata else 0
+        self._check(self._L.sea_b200_decode_range(self._h, buf.ctypes.data, buf.size, first_frame, n_frames, flags, None, 0, C.byref(n),
+                                                  C.byref(rate), C.byref(ch)))
+        out = np.empty(max(int(n.value), 1), dtype=np.int16)
+        self._check(self._L.sea_b200_decode_range(self._h, buf.ctypes.data, buf.size, first_frame, n_frames, flags, out.ctypes.data,
+                                                  out.size, C.byref(n), C.byref(rate), C.byref(ch)))
         return SeaDecodeInfo(out[: n.value], rate.value, ch.value)
 
     # ---- batch, host buffers ---------------------------------------------------------------------------------
@@ -453,6 +476,33 @@ class SeaEncoder:
             self.state = self.FINISHED
         return not eof
 
+    def encode_frames(self, max_chunks: int) -> bool:
+        """Up to max_chunks encode_frame() steps in ONE launch (sea_b200_encoder_make_chunks): same bytes, same state machine,
+        one H2D / kernel / D2H per call instead of one per chunk.  Returns True while more input is expected."""
+        if self.state == self.FINISHED:
+            raise SeaError(ERR_ENCODER_CLOSED)
+        fpc = self.settings.frames_per_chunk
+        want = fpc * max_chunks
+        frames = min(want, self.total_frames - self.written_frames) if self.total_frames > 0 else want
+        raw = _read_max_or_zero(self.reader, frames * self.channels * 2)
+        if len(raw) % (2 * self.channels) != 0:
+            raise SeaError(ERR_IO, "UnexpectedEof (encoder.rs:95-99)")
+        samples = np.ascontiguousarray(np.frombuffer(raw, dtype="<i2"))
+        eof = samples.size == 0 or samples.size < want * self.channels
+        if samples.size:
+            out = np.empty(70000 * max_chunks, dtype=np.uint8)
+            n, nck = C.c_uint64(0), C.c_uint32(0)
+            self._ctx._check(self._L.sea_b200_encoder_make_chunks(self._h, samples.ctypes.data, samples.size, out.ctypes.data, out.size,
+                                                                  C.byref(n), C.byref(nck)))
+            if self.state == self.START:
+                self.writer.write(_serialize_header(self.channels, self.chunk_size, fpc, self.sample_rate, self.total_frames))
+                self.state = self.WRITING
+            self.writer.write(out[: n.value].tobytes())
+            self.written_frames += samples.size // self.channels
+        if eof:
+            self.state = self.FINISHED
+        return not eof
+
     def flush(self):
         if hasattr(self.writer, "flush"):
             self.writer.flush()
@@ -503,6 +553,24 @@ class SeaDecoder:
         n = C.c_uint64(0)
         self._ctx._check(self._L.sea_b200_decoder_decode_chunk(self._h, buf.ctypes.data, buf.size, remaining, out.ctypes.data, out.size,
                                                                C.byref(n)))
+        self.frames_read += n.value // h.channels
+        self.writer.write(out[: n.value].astype("<i2").tobytes())
+        return True
+
+    def decode_frames(self, max_chunks: int) -> bool:
+        """Up to max_chunks decode_frame() steps in one chunk-parallel launch (sea_b200_decoder_decode_chunks)."""
+        h = self.header
+        if h.total_frames != 0 and h.total_frames <= self.frames_read:
+            return False
+        remaining = h.total_frames - self.frames_read if h.total_frames > 0 else -1
+        encoded = _read_max_or_zero(self.reader, h.chunk_size * max_chunks)
+        if not encoded:
+            return False
+        buf = np.frombuffer(encoded, dtype=np.uint8)
+        out = np.empty(h.frames_per_chunk * h.channels * max_chunks, dtype=np.int16)
+        n = C.c_uint64(0)
+        self._ctx._check(self._L.sea_b200_decoder_decode_chunks(self._h, self._ctx._h, buf.ctypes.data, buf.size, remaining,
+                                                                out.ctypes.data, out.size, C.byref(n)))
         self.frames_read += n.value // h.channels
         self.writer.write(out[: n.value].astype("<i2").tobytes())
         return True

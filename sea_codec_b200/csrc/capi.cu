@@ -888,35 +888,47 @@ void sea_b200_encoder_destroy(sea_b200_encoder *enc)
     delete enc;
 }
 
-int sea_b200_encoder_make_chunk(sea_b200_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint8_t *out, uint64_t out_cap,
-                                uint64_t *out_len)
+int sea_b200_encoder_make_chunks(sea_b200_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint8_t *out, uint64_t out_cap,
+                                 uint64_t *out_len, uint32_t *n_chunks)
 {
     if (!enc || !pcm || !out || !out_len) return SEA_B200_ERR_INVALID_PARAMETERS;
     sea_b200_ctx *ctx = enc->ctx;
     const EncodePlan &pl = enc->plan;
     if (n_samples == 0 || n_samples % enc->channels) return fail(ctx, SEA_B200_ERR_INVALID_PARAMETERS, "make_chunk needs whole frames");
     const uint64_t frames64 = n_samples / enc->channels;
-    if (frames64 > pl.N) return fail(ctx, SEA_B200_ERR_DOMAIN, "more than frames_per_chunk frames (file.rs:173-175 assert)");
+    if (frames64 > 0xffffffffull) return fail(ctx, SEA_B200_ERR_TOO_MANY_FRAMES, "more than 2^32 frames in one call");
     CU(cudaSetDevice(ctx->device));
     const uint32_t frames = (uint32_t)frames64;
+    const uint32_t chunks = (frames + pl.N - 1) / pl.N;
     const uint64_t zero = 0;
     EncodeJob job;
     int rc = plan_encode(ctx, 1, &zero, &frames, enc->sample_rate, enc->channels, &enc->settings, &zero, true, &job);
     if (rc) return rc;
     CU(ctx->in.reserve(n_samples * 2 + 64));
-    CU(ctx->out.reserve(pl.max_chunk_bytes + 64));
+    CU(ctx->out.reserve((uint64_t)chunks * pl.max_chunk_bytes + 64));
     CU(cudaMemcpyAsync(ctx->in.p, pcm, n_samples * 2, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t len = 0;
-    rc = run_encode(ctx, job, ctx->in.as<int16_t>(), ctx->out.as<uint8_t>(), enc->d_state, &len, nullptr);
+    uint32_t first = 0;
+    rc = run_encode(ctx, job, ctx->in.as<int16_t>(), ctx->out.as<uint8_t>(), enc->d_state, &len, &first);
     if (rc) return rc;
     if (len > out_cap) return fail(ctx, SEA_B200_ERR_CAPACITY, "chunk buffer too small");
     CU(cudaMemcpyAsync(out, ctx->out.p, len, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (enc->chunk_size == 0) enc->chunk_size = (uint32_t)len & 0xffffu;  // file.rs:166-168 (`as u16`)
-    if (frames == pl.N && enc->chunk_size != ((uint32_t)len & 0xffffu))
+    if (enc->chunk_size == 0) enc->chunk_size = first & 0xffffu;  // file.rs:166-168 (`as u16`)
+    if (frames >= pl.N && enc->chunk_size != (first & 0xffffu))
         return fail(ctx, SEA_B200_ERR_DOMAIN, "full chunk size differs from header.chunk_size (file.rs:173-175 assert)");
     *out_len = len;
+    if (n_chunks) *n_chunks = chunks;
     return SEA_B200_OK;
+}
+
+int sea_b200_encoder_make_chunk(sea_b200_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint8_t *out, uint64_t out_cap,
+                                uint64_t *out_len)
+{
+    if (!enc) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (n_samples / (enc->channels ? enc->channels : 1) > enc->plan.N)
+        return fail(enc->ctx, SEA_B200_ERR_DOMAIN, "more than frames_per_chunk frames (file.rs:173-175 assert)");
+    return sea_b200_encoder_make_chunks(enc, pcm, n_samples, out, out_cap, out_len, nullptr);
 }
 
 int sea_b200_decoder_create(sea_b200_ctx *ctx, const uint8_t *header22, uint64_t len, sea_b200_decoder **out)

@@ -537,7 +537,8 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
 
         const uint32_t chunk_bytes = res_sec_bit / 8u + (sh_res_bits + 7u) / 8u;
         if (chunk_bytes > p.max_chunk_bytes) enc_report(err, kDevDomain);
-        uint8_t *dst = out + st.out_off + (p.raw_chunk_mode ? 0 : (uint64_t)kFileHeaderBytes + (uint64_t)k * p.full_chunk_bytes);
+        // raw chunk mode (make_chunk seam): no file header; consecutive chunks of one call follow each other
+        uint8_t *dst = out + st.out_off + (p.raw_chunk_mode ? 0 : (uint64_t)kFileHeaderBytes) + (uint64_t)k * p.full_chunk_bytes;
         for (uint32_t i = tid; i < chunk_bytes && i < p.max_chunk_bytes; i += T)
             dst[i] = (uint8_t)(chunk_buf[i >> 2] >> (24u - 8u * (i & 3u)));
         if (k == 0) first_chunk_bytes = chunk_bytes;

@@ -1,0 +1,142 @@
+"""GPU tests of the SURVEY 8f "next" rows built on the hot path: seaconv conversions (f1), multi-chunk streaming (f2), the
+wasm_api / c/sea.h shaped entry points (f3) and random-access decode (f4).  Every result is compared with the CPU oracle."""
+import ctypes as C
+import io
+import os
+
+import numpy as np
+import pytest
+
+import sea_codec_b200 as S
+from sea_codec_b200 import api, seaconv, synth, wav
+
+pytestmark = pytest.mark.gpu
+
+
+def test_seaconv_wav_to_sea_and_back(ctx, oracle, tmp_path):
+    pcm = synth.gen_stream(7, 44100 * 3 + 123, 2, 44100)
+    wav_in, sea_out, wav_out = str(tmp_path / "in.wav"), str(tmp_path / "out.sea"), str(tmp_path / "back.wav")
+    wav.write_wav(pcm, 2, 44100, wav_in)
+    for argv, kw in ((["-b", "3"], dict(residual_bits=3.0)), (["-b", "2.5", "-v", "-c", "2000", "-d", "10", "-s", "5"],
+                                                               dict(residual_bits=2.5, vbr=True, frames_per_chunk=2000,
+                                                                    scale_factor_frames=10, scale_factor_bits=5))):
+        assert seaconv.main([wav_in, sea_out] + argv + ["--chunks-per-launch", "7"]) == 0
+        got = open(sea_out, "rb").read()
+        assert got == oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(**kw)), argv
+        assert seaconv.main([sea_out, wav_out, "--chunks-per-launch", "5"]) == 0
+        back = wav.read_wav(wav_out)
+        assert back.channels == 2 and back.sample_rate == 44100
+        assert np.array_equal(back.samples, oracle.sea_decode(got).samples)
+
+
+@pytest.mark.parametrize("vbr", [False, True])
+def test_multi_chunk_streaming_equals_chunk_at_a_time(ctx, oracle, vbr):
+    ch, frames = 2, 5120 * 9 + 1000
+    pcm = synth.gen_stream(3, frames, ch, 48000)
+    st = S.EncoderSettings(residual_bits=3.0, vbr=vbr)
+    ref = oracle.sea_encode(pcm, 48000, ch, oracle.make_settings(3.0, vbr=vbr))
+    for per, total in ((1, frames), (4, frames), (64, frames), (3, None)):
+        out = io.BytesIO()
+        src = pcm if total is not None else pcm[: 5120 * 9 * ch]  # streaming header: whole chunks only
+        enc = S.SeaEncoder(ch, 48000, total, st, io.BytesIO(src.astype("<i2").tobytes()), out, ctx=ctx)
+        while enc.encode_frames(per):
+            pass
+        enc.finalize()
+        enc.close()
+        if total is not None:
+            assert out.getvalue() == ref, f"{per} chunks per launch"
+        else:
+            want = oracle.sea_encode(src, 48000, ch, oracle.make_settings(3.0, vbr=vbr))
+            assert out.getvalue()[22:] == want[22:]  # same chunks; the streaming header carries total_frames = 0
+            assert out.getvalue()[14:18] == b"\x00\x00\x00\x00"
+    want_pcm = oracle.sea_decode(ref).samples
+    for per in (1, 2, 5, 100):
+        pcm_out = io.BytesIO()
+        dec = S.SeaDecoder(io.BytesIO(ref), pcm_out, ctx=ctx)
+        while dec.decode_frames(per):
+            pass
+        dec.close()
+        assert np.array_equal(np.frombuffer(pcm_out.getvalue(), dtype="<i2"), want_pcm), f"{per} chunks per launch"
+
+
+def test_decode_range_random_access(ctx, oracle):
+    ch, frames = 2, 5120 * 6 + 777
+    pcm = synth.gen_stream(11, frames, ch, 44100)
+    for kw in (dict(residual_bits=3.0), dict(residual_bits=3.5, vbr=True)):
+        sea = oracle.sea_encode(pcm, 44100, ch, oracle.make_settings(**kw))
+        full = oracle.sea_decode(sea).samples.reshape(-1, ch)
+        for first, n in ((0, 1), (0, frames), (5119, 2), (5120, 5120), (100, 20000), (5120 * 6, 777), (5120 * 6 + 700, 5000),
+                         (frames - 1, 1), (frames, 10), (12345, 0), (1 << 40, 5)):
+            got = ctx.decode_range(sea, first, n)
+            want = full[first: first + n].reshape(-1) if first < frames else np.zeros(0, dtype=np.int16)
+            assert got.sample_rate == 44100 and got.channels == ch
+            assert np.array_equal(got.samples, want), (kw, first, n)
+    # metadata: the reference never skips it (file.rs:53-54); the flag is the format-compatible fix
+    sea = oracle.sea_encode(pcm, 44100, ch, oracle.make_settings(3.0))
+    meta = b"title=x\nartist=y"
+    with_meta = sea[:18] + len(meta).to_bytes(4, "little") + meta + sea[22:]
+    got = ctx.decode_range(with_meta, 6000, 3000, skip_metadata=True)
+    assert np.array_equal(got.samples, oracle.sea_decode(sea).samples.reshape(-1, ch)[6000:9000].reshape(-1))
+
+
+def test_wasm_api_and_csea_shaped_entry_points(ctx, oracle):
+    L = S.lib()
+    pcm = synth.gen_stream(5, 5120 * 2 + 300, 2, 44100)
+    L.sea_b200_wasm_setup()
+    for bitrate, vbr in ((3.0, False), (4.0, True)):
+        cap = pcm.size * 2 + 4096
+        buf = L.sea_b200_wasm_allocate(cap)
+        assert buf
+        n = L.sea_b200_wasm_sea_encode(pcm.ctypes.data, pcm.size * 2, 44100, 2, bitrate, vbr, buf, cap)
+        assert n > 0 and L.sea_b200_wasm_status() == 0
+        enc = C.string_at(buf, n)
+        assert enc == oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(bitrate, vbr=vbr))
+        out = np.zeros(pcm.size, dtype=np.int16)
+        rate, ch = C.c_uint32(0), C.c_uint32(0)
+        nb = L.sea_b200_wasm_sea_decode(buf, n, out.ctypes.data, out.size * 2, C.byref(rate), C.byref(ch))
+        assert nb == pcm.size * 2 and (rate.value, ch.value) == (44100, 2)
+        assert np.array_equal(out, oracle.sea_decode(enc).samples)
+        # too small an output buffer: the reference asserts (wasm_api.rs:58,81); here 0 + a status
+        assert L.sea_b200_wasm_sea_decode(buf, n, out.ctypes.data, 100, C.byref(rate), C.byref(ch)) == 0
+        assert L.sea_b200_wasm_status() == api.ERR_CAPACITY
+        L.sea_b200_wasm_deallocate(buf, cap)
+    # c/sea.h: two-call pattern, return codes 0 / 1 / 2
+    enc = np.frombuffer(oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(3.0)), dtype=np.uint8).copy()
+    rate, ch, tf = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    assert L.sea_b200_csea_decode(enc.ctypes.data, enc.size, C.byref(rate), C.byref(ch), None, C.byref(tf)) == 0
+    assert (rate.value, ch.value, tf.value) == (44100, 2, pcm.size // 2)
+    out = np.zeros(tf.value * ch.value, dtype=np.int16)
+    assert L.sea_b200_csea_decode(enc.ctypes.data, enc.size, C.byref(rate), C.byref(ch), out.ctypes.data, C.byref(tf)) == 0
+    assert np.array_equal(out, oracle.sea_decode(enc.tobytes()).samples)
+    bad = enc.copy()
+    bad[0] = ord("x")
+    assert L.sea_b200_csea_decode(bad.ctypes.data, bad.size, C.byref(rate), C.byref(ch), out.ctypes.data, C.byref(tf)) == 1
+    short = enc[: enc.size // 2].copy()
+    assert L.sea_b200_csea_decode(short.ctypes.data, short.size, C.byref(rate), C.byref(ch), out.ctypes.data, C.byref(tf)) == 2
+
+
+def test_cpp_seaconv_matches_python_cli(ctx, oracle, tmp_path):
+    """tools/seaconv.cpp (compiled host, include/sea_b200.hpp) produces the same files as the oracle / the Python CLI."""
+    import subprocess
+
+    from sea_codec_b200 import build as B
+    from util import ROOT
+
+    exe = os.path.join(ROOT, "tests", "build", "seaconv")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    lib_dir = os.path.dirname(B.LIB)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tools", "seaconv.cpp"),
+                    "-L" + lib_dir, "-l:libsea_b200.so", "-Wl,-rpath," + lib_dir], check=True)
+    pcm = synth.gen_stream(21, 44100 + 321, 1, 22050)
+    wav_in, sea_out, wav_out = str(tmp_path / "in.wav"), str(tmp_path / "out.sea"), str(tmp_path / "back.wav")
+    wav.write_wav(pcm, 1, 22050, wav_in)
+    r = subprocess.run([exe, wav_in, sea_out, "-b", "4", "-c", "4000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    enc = open(sea_out, "rb").read()
+    assert enc == oracle.sea_encode(pcm, 22050, 1, oracle.make_settings(4.0, frames_per_chunk=4000))
+    r = subprocess.run([exe, sea_out, wav_out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    back = wav.read_wav(wav_out)
+    assert back.sample_rate == 22050 and back.channels == 1 and np.array_equal(back.samples, oracle.sea_decode(enc).samples)
+    r = subprocess.run([exe, wav_in, sea_out, "-b", "9"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Bitrate must be between 1.0 and 8.0" in r.stderr
