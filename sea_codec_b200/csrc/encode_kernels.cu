@@ -236,6 +236,15 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             }
         }
         __syncwarp();
+        // the chain's LMS state and previous scale factor live in registers for the whole pass (identical in the 16 lanes of
+        // the chain group); shared memory holds them only between passes and chunks
+        int32_t cw[4], chh[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cw[i] = st_w[c * 4 + i];
+            chh[i] = st_h[c * 4 + i];
+        }
+        uint32_t prev = (uint32_t)st_prev[c];
         for (uint32_t blk = 0; blk < nblk; blk++) {
             uint32_t nf = frames - blk * F;
             if (nf > F) nf = F;
@@ -254,13 +263,14 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const int32_t *row = fl.lut + fl.slot_off[slot] + lane;  // [code][lane]: both chains of the warp read their own banks
             const uint32_t kmax = (1u << (size - 1u)) - 1u;
 
-            int32_t w[4], h[4];
+            // every candidate starts from the chain's state (kept in registers: the winner broadcasts it at the end of the block)
+            int32_t w[4], h[4], sg[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                w[i] = st_w[c * 4 + i];
-                h[i] = st_h[c * 4 + i];
+                w[i] = cw[i];
+                h[i] = chh[i];
+                sg[i] = (h[i] >> 31) | 1;  // lms.rs:45-46 sign of the history, carried along instead of recomputed per tap
             }
-            const uint32_t prev = (uint32_t)st_prev[c];
             const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
             unsigned long long rank = 0;
             const int16_t *xs = xbuf + grp * F;
@@ -271,7 +281,10 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
 #pragma unroll 4
                 for (uint32_t f = 0; f < nf; f++) {
                     const int32_t xv = xs[f];
-                    const int32_t pr = lms_predict(w, h);
+                    // lms.rs:33-41 as a two-level sum (wrapping adds associate): the newest history value enters last
+                    const uint32_t acc = ((uint32_t)w[0] * (uint32_t)h[0] + (uint32_t)w[1] * (uint32_t)h[1]) +
+                                         ((uint32_t)w[2] * (uint32_t)h[2] + (uint32_t)w[3] * (uint32_t)h[3]);
+                    const int32_t pr = (int32_t)acc >> 13;
                     const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
                     const int32_t n = (int32_t)(((int64_t)r * (int64_t)recip + 32768) >> 16);
                     const uint32_t an = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;
@@ -280,35 +293,40 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     if ((FB > 0 ? (uint32_t)FB : size) == 2u) k = an >= 3u ? 1u : 0u;
                     const uint32_t code = 2u * k + ((uint32_t)r >> 31);
                     const int32_t d = row[code << 5];
-                    const int32_t y = clamp_i16((int32_t)((uint32_t)pr + (uint32_t)d));
+                    const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
+                    const int32_t y = clamp_i16(v);
                     rank = rank_step<kNarrow>(rank, xv - y, w);
-                    lms_update(w, h, y, d);
+                    const int32_t delta = d >> 4;  // lms.rs:43-51
+#pragma unroll
+                    for (int i = 0; i < 4; i++) w[i] += delta * sg[i];
+                    h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = y;
+                    sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (v >> 31) | 1;  // the clamp keeps the sign
                     cbuf[(size_t)f * T] = (uint8_t)code;
                 }
             };
             if (__all_sync(0xffffffffu, weights_stay_narrow(w, F))) trial(NarrowTag<true>{});
             else trial(NarrowTag<false>{});
-            // arg-min over the 16 candidates of the chain: strict total order (rank, ord)
+            // arg-min over the 16 candidates of the chain: strict total order (rank, ord); ord follows from the lane
             unsigned long long g_rank = rank;
-            uint32_t g_ord = ord, g_lane = lane;
+            uint32_t g_lane = lane;
 #pragma unroll
             for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
                 const unsigned long long o_rank = __shfl_xor_sync(0xffffffffu, g_rank, o);
-                const uint32_t o_ord = __shfl_xor_sync(0xffffffffu, g_ord, o);
                 const uint32_t o_lane = __shfl_xor_sync(0xffffffffu, g_lane, o);
+                const uint32_t g_ord = ((g_lane & 15u) - prev) & (nsf - 1u), o_ord = ((o_lane & 15u) - prev) & (nsf - 1u);
                 if (o_rank < g_rank || (o_rank == g_rank && o_ord < g_ord)) {
                     g_rank = o_rank;
-                    g_ord = o_ord;
                     g_lane = o_lane;
                 }
             }
-            if (active && lane == g_lane) {  // encoder_base.rs:181-186: persist the winner
+            // encoder_base.rs:181-186: the winner's state becomes the chain's state -- broadcast in registers
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    st_w[c * 4 + i] = w[i];
-                    st_h[c * 4 + i] = h[i];
-                }
-                st_prev[c] = (int32_t)sf;
+            for (int i = 0; i < 4; i++) {
+                cw[i] = __shfl_sync(0xffffffffu, w[i], g_lane);
+                chh[i] = __shfl_sync(0xffffffffu, h[i], g_lane);
+            }
+            prev = g_lane & 15u;
+            if (active && lane == g_lane) {
                 if (mode == 1) vs.keys[blk * C + c] = rank;
                 else put_bits(chunk_buf, sf_sec_bit + (blk * C + c) * s, s, sf);
             }
@@ -325,16 +343,26 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     prefix = c * size;
                 }
                 const uint8_t *wbuf = codes + (threadIdx.x - lane + g_lane);
+                __syncwarp(__activemask());  // the winner's codes were written by another lane
                 for (uint32_t f = sf; f < nf; f += lpc)
                     put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[(size_t)f * T]);
             }
-            __syncwarp();  // everybody is done with this block's samples, codes and state
+            __syncwarp();  // everybody is done with this block's samples and codes
             if (pre) {
                 xbuf[lane] = (int16_t)nx0;
                 xbuf[F + lane] = (int16_t)nx1;
             }
             __syncwarp();
         }
+        if (active && sf == 0u) {  // hand the state to the next pass / chunk
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                st_w[c * 4 + i] = cw[i];
+                st_h[c * 4 + i] = chh[i];
+            }
+            st_prev[c] = (int32_t)prev;
+        }
+        __syncwarp();
     }
 }
 

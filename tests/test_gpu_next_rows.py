@@ -140,3 +140,38 @@ def test_cpp_seaconv_matches_python_cli(ctx, oracle, tmp_path):
     assert back.sample_rate == 22050 and back.channels == 1 and np.array_equal(back.samples, oracle.sea_decode(enc).samples)
     r = subprocess.run([exe, wav_in, sea_out, "-b", "9"], capture_output=True, text=True)
     assert r.returncode == 1 and "Bitrate must be between 1.0 and 8.0" in r.stderr
+
+
+def test_baseline_config2_vbr_mono_full_size(ctx, oracle):
+    """BASELINE.json configs[1]: VBR, mono 48 kHz 60 s synthetic tone+noise, bitrate 3 -- bit-exact encode and decode at full
+    size (2 880 000 samples: 562 full chunks of 1922 bytes + one of 2560 frames)."""
+    frames = 48000 * 60
+    pcm = synth.gen_stream(2, frames, 1, 48000)
+    enc = ctx.sea_encode(pcm, 48000, 1, S.EncoderSettings(residual_bits=3.0, vbr=True))
+    assert ctx.last_vbr_ties == 0, "error ties across a bucket boundary: the reference's sort order would be unspecified here"
+    ref = oracle.sea_encode(pcm, 48000, 1, oracle.make_settings(3.0, vbr=True))
+    assert enc == ref
+    hdr = S.parse_header(enc)
+    assert hdr.chunk_size == 1922 and len(enc) == 22 + 562 * 1922 + (len(enc) - 22 - 562 * 1922) and (frames - 562 * 5120) == 2560
+    dec = ctx.sea_decode(enc)
+    assert dec.sample_rate == 48000 and dec.channels == 1
+    assert np.array_equal(dec.samples, oracle.sea_decode(ref).samples)
+
+
+def test_baseline_config3_eight_channels_cbr4(ctx, oracle):
+    """BASELINE.json configs[2]: 8-channel 48 kHz interleaved stream, CBR bitrate 4 (multichannel lane mapping, chunk-parallel
+    decode) at full size: 14.4 M frames, 2812 full chunks of 21 636 bytes + one of 2560 frames."""
+    ch, frames = 8, 48000 * 300
+    pcm = synth.gen_stream(3, frames, ch, 48000)
+    enc = ctx.sea_encode(pcm, 48000, ch, S.EncoderSettings(residual_bits=4.0))
+    ref = oracle.sea_encode(pcm, 48000, ch, oracle.make_settings(4.0))
+    assert S.parse_header(enc).chunk_size == 21636 and len(enc) == 22 + 2812 * 21636 + 10884
+    assert enc == ref
+    dec = ctx.sea_decode(enc)
+    want = oracle.sea_decode(ref).samples
+    assert np.array_equal(dec.samples, want)
+    # chunk-parallel property: any chunk range decodes to the same samples as the whole stream (what a 2nd GPU would do)
+    n_chunks = (frames + 5119) // 5120
+    for k0, k1 in ((0, 1), (1000, 1407), (n_chunks - 3, n_chunks)):
+        part = ctx.decode_range(enc, k0 * 5120, (k1 - k0) * 5120)
+        assert np.array_equal(part.samples, want[k0 * 5120 * ch: min(frames, k1 * 5120) * ch])
