@@ -13,6 +13,11 @@ ch = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 dev = torch.device("cuda:0")
 ctx = S.Context(0)
+if os.environ.get("PROBE_STREAM") == "default":
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # the legacy default stream
+elif os.environ.get("PROBE_STREAM") == "torch":
+    _ts = torch.cuda.Stream()
+    ctx.set_stream(_ts.cuda_stream)
 frames = int(sys.argv[6]) if len(sys.argv) > 6 else secs * 44100  # argv[6]: exact frame count (e.g. a multiple of 5120: no partial chunk)
 st = S.EncoderSettings(residual_bits=bits)
 u = min(n, 16)
@@ -33,6 +38,7 @@ for i in range(iters):
 ok = bool(torch.equal(out.view(n, spp)[:u].view(u, frames, ch), pcm.view(u, frames, ch)) is False)  # lossy codec: only replica equality below
 rep = torch.equal(out.view(n, spp)[n - 1], out.view(n, spp)[(n - 1) % u])
 best = min(ms[1:]) if len(ms) > 1 else ms[0]
+print("all iterations (ms):", " ".join(f"{m:.3f}" for m in ms))
 alg = n * bound + 2 * n * spp
 print(f"lib={os.path.basename(os.environ.get('SEA_B200_LIB', 'default'))} n={n} ch={ch} bits={bits}: best {best:.3f} ms  "
       f"{n*spp/best/1e3:.0f} Msamples/s  {alg/best/1e6:.0f} GB/s ({alg/best/1e6/6550.4*100:.1f}% of HBM peak) replicas_equal={rep}")
