@@ -175,3 +175,44 @@ def test_baseline_config3_eight_channels_cbr4(ctx, oracle):
     for k0, k1 in ((0, 1), (1000, 1407), (n_chunks - 3, n_chunks)):
         part = ctx.decode_range(enc, k0 * 5120, (k1 - k0) * 5120)
         assert np.array_equal(part.samples, want[k0 * 5120 * ch: min(frames, k1 * 5120) * ch])
+
+
+def test_randomised_settings_against_oracle(ctx, oracle):
+    """Seeded sweep over the parameter space the grid tests do not enumerate: channels 1-5, scale_factor_bits 2-6, block and
+    chunk geometry, CBR 1-8 and VBR 1.5-7.3 bits, ragged lengths, loud / quiet / clipped signals.  Encode bytes and decoded PCM
+    must equal the oracle's; settings the reference cannot run (it would panic) must be rejected, not mis-encoded."""
+    rng = np.random.default_rng(20261018)
+    checked = rejected = 0
+    for case in range(48):
+        ch = int(rng.integers(1, 6))
+        sfb = int(rng.integers(2, 7))
+        sff = int(rng.choice([5, 8, 10, 16, 20, 25, 32, 40]))
+        fpc = sff * int(rng.integers(8, 200))
+        if fpc > 32000:
+            fpc = sff * 100
+        vbr = bool(rng.integers(0, 2))
+        bits = float(rng.choice([1.5, 2.0, 2.5, 3.0, 3.7, 4.2, 5.0, 6.5, 7.3])) if vbr else float(rng.integers(1, 9))
+        frames = int(rng.integers(1, 3 * fpc + 50))
+        kind = case % 4
+        t = np.arange(frames * ch, dtype=np.float64)
+        if kind == 0:
+            pcm = synth.gen_stream(1000 + case, frames, ch, 44100)
+        elif kind == 1:  # loud, clipping
+            pcm = np.clip(40000 * np.sin(t * 0.05) + rng.normal(0, 3000, t.size), -32768, 32767).astype(np.int16)
+        elif kind == 2:  # quiet
+            pcm = rng.integers(-40, 41, t.size).astype(np.int16)
+        else:  # white noise, full scale
+            pcm = rng.integers(-32768, 32768, t.size).astype(np.int16)
+        kw = dict(residual_bits=bits, vbr=vbr, scale_factor_bits=sfb, scale_factor_frames=sff, frames_per_chunk=fpc)
+        try:
+            enc = ctx.sea_encode(pcm, 44100, ch, S.EncoderSettings(**kw))
+        except api.SeaError as e:
+            assert e.code in (api.ERR_DOMAIN, api.ERR_INVALID_PARAMETERS), (kw, e)
+            rejected += 1
+            continue
+        ref = oracle.sea_encode(pcm, 44100, ch, oracle.make_settings(**kw))
+        assert enc == ref, (case, ch, frames, kw)
+        dec = ctx.sea_decode(enc)
+        assert np.array_equal(dec.samples, oracle.sea_decode(ref).samples), (case, ch, frames, kw)
+        checked += 1
+    assert checked >= 30, (checked, rejected)
