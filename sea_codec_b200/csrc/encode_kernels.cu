@@ -195,6 +195,29 @@ __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p,
 // the PCM sample inside the 20-step recurrence.  Here the block's samples are staged through shared memory one block ahead, the
 // dequant rows live in shared memory as [size][code][sf] (the lane's sf is fixed), FB > 0 makes the residual size a compile-time
 // constant, and err^2 / penalty^2 are accumulated with 64-bit fused multiply-adds.
+// Where the fast pass keeps its dequant rows.  One CTA per stream and ~7 streams per SM at the benchmark's 1024 streams: the
+// tables must leave room for that many CTAs (a [code][32 lanes] table of size 8 alone is 32 KB; 3 CTAs per SM cost 2-3x at the
+// high bitrates).  kEncLut32: [code][lane], conflict free.  kEncLut16: [code][sf], the two chains of a warp share a row (same
+// scale factors; occasional 2-way conflicts).  kEncLutGlobal: the table as uploaded, read with ld.global.nc (L1 resident;
+// slower per step than shared memory, so only when nothing else fits).
+enum : int { kEncLut32 = 0, kEncLut16 = 1, kEncLutGlobal = 2 };
+__host__ __device__ inline uint32_t enc_lut_entries(int fb, uint32_t vbr_base)  // sum over the sizes in use of 2^size
+{
+    if (fb > 0) return 1u << fb;
+    const uint32_t lo = vbr_base > 1u ? vbr_base - 1u : 1u;
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < 4u; i++)
+        if (lo + i <= 8u) n += 1u << (lo + i);
+    return n;
+}
+// CBR: a function of the residual size alone (compile-time in encode_kernel<FB>); VBR: chosen by the host from the CTA's total
+// shared memory (launch_encode_generic) and passed in EncParams::lut_mode.
+__host__ __device__ constexpr int enc_lut_mode_cbr(int fb) { return fb <= 7 ? kEncLut32 : kEncLut16; }
+template <int M>
+struct LutTag {
+    static constexpr int value = M;
+};
+
 template <bool V>
 struct NarrowTag {
     static constexpr bool value = V;
@@ -205,6 +228,7 @@ struct FastLut {
     const int32_t *recip;   // shared memory: [slot][16]
     uint32_t slot_off[4];   // word offset of the table of size lo_size + i
     uint32_t lo_size;
+    int mode;               // kEncLut32 / kEncLut16 / kEncLutGlobal
 };
 
 template <int FB>
@@ -260,7 +284,9 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const uint32_t size = FB > 0 ? (uint32_t)FB : (mode == 2 ? (uint32_t)vs.sizes[blk * C + c] : uniform_size);
             const uint32_t slot = FB > 0 ? 0u : size - fl.lo_size;
             const int32_t recip = fl.recip[slot * 16u + sf];
-            const int32_t *row = fl.lut + fl.slot_off[slot] + lane;  // [code][lane]: both chains of the warp read their own banks
+            // shared [code][lane] / [code][sf] (two chains share a row) / global [sf][code]: see kEncLut*
+            const int32_t *row = fl.mode == kEncLutGlobal ? tab + tab_dqt_off(4, size) + (sf << size)
+                                                          : fl.lut + (fl.mode == kEncLut32 ? fl.slot_off[slot] + lane : (fl.slot_off[slot] >> 1) + sf);
             const uint32_t kmax = (1u << (size - 1u)) - 1u;
 
             // every candidate starts from the chain's state (kept in registers: the winner broadcasts it at the end of the block)
@@ -276,8 +302,9 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const int16_t *xs = xbuf + grp * F;
             uint8_t *cbuf = codes + threadIdx.x;
             // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
-            auto trial = [&](auto narrow_tag) {
+            auto trial = [&](auto narrow_tag, auto lut_tag) {
                 constexpr bool kNarrow = decltype(narrow_tag)::value;
+                constexpr int kMode = decltype(lut_tag)::value;
 #pragma unroll 4
                 for (uint32_t f = 0; f < nf; f++) {
                     const int32_t xv = xs[f];
@@ -292,7 +319,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     k = k < kmax ? k : kmax;
                     if ((FB > 0 ? (uint32_t)FB : size) == 2u) k = an >= 3u ? 1u : 0u;
                     const uint32_t code = 2u * k + ((uint32_t)r >> 31);
-                    const int32_t d = row[code << 5];
+                    const int32_t d = kMode == kEncLutGlobal ? __ldg(row + code) : row[code << (kMode == kEncLut32 ? 5 : 4)];
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
                     const int32_t y = clamp_i16(v);
                     rank = rank_step<kNarrow>(rank, xv - y, w);
@@ -304,8 +331,15 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     cbuf[(size_t)f * T] = (uint8_t)code;
                 }
             };
-            if (__all_sync(0xffffffffu, weights_stay_narrow(w, F))) trial(NarrowTag<true>{});
-            else trial(NarrowTag<false>{});
+            const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
+            auto run = [&](auto lut_tag) {
+                if (narrow) trial(NarrowTag<true>{}, lut_tag);
+                else trial(NarrowTag<false>{}, lut_tag);
+            };
+            if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1)>{});
+            else if (fl.mode == kEncLut32) run(LutTag<kEncLut32>{});
+            else if (fl.mode == kEncLut16) run(LutTag<kEncLut16>{});
+            else run(LutTag<kEncLutGlobal>{});
             // arg-min over the 16 candidates of the chain: strict total order (rank, ord); ord follows from the lane
             unsigned long long g_rank = rank;
             uint32_t g_lane = lane;
@@ -423,16 +457,22 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
         fl.lut = lut;
         fl.recip = rcp;
         fl.lo_size = FB > 0 ? (uint32_t)FB : (p.base > 1u ? p.base - 1u : 1u);
+        fl.mode = FB > 0 ? enc_lut_mode_cbr(FB > 0 ? FB : 1) : (int)p.lut_mode;
         const uint32_t n_slots = FB > 0 ? 1u : 4u;
         uint32_t off = 0;
         for (uint32_t i = 0; i < n_slots; i++) {
             const uint32_t size = fl.lo_size + i;
             fl.slot_off[i] = off;
             if (size <= 8u) {
-                const uint32_t n = 32u << size;
-                for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 5)];
                 for (uint32_t e = tid; e < 16u; e += T) rcp[i * 16u + e] = tab[tab_recip_off(4, size) + e];
-                off += n;
+                if (fl.mode == kEncLut32) {
+                    const uint32_t n = 32u << size;
+                    for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 5)];
+                } else if (fl.mode == kEncLut16) {
+                    const uint32_t n = 16u << size;
+                    for (uint32_t e = tid; e < n; e += T) lut[(off >> 1) + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 4)];
+                }
+                off += 32u << size;  // slot offsets are kept in [code][32] units; kEncLut16 halves them
             }
         }
     }
@@ -610,6 +650,10 @@ static cudaError_t launch_encode_t(const int16_t *d_pcm, uint8_t *d_out, const E
 {
     cudaError_t e = cudaFuncSetAttribute(encode_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // one CTA per stream: residency is bounded by shared memory, so ask for the largest carve-out (the driver's default picked
+    // 164 KB of the 228 KB and left a second wave at the high bitrates)
+    e = cudaFuncSetAttribute(encode_kernel<FB>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     encode_kernel<FB><<<p.n_streams, T, smem, stream>>>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err);
     return cudaGetLastError();
 }
@@ -626,19 +670,23 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + ((2u * (size_t)p.F * T + 15u) & ~(size_t)15u) + 16u;
     // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
     const bool fast = p.s == 4u && p.F <= 32u && p.channels <= 16u;
+    int lut_mode = kEncLut32;
     if (fast) {
         smem += ((size_t)warps * 2u * p.F * 2u + 15u) & ~(size_t)15u;
-        if (p.vbr) {
-            const uint32_t lo = p.base > 1u ? p.base - 1u : 1u;
-            for (uint32_t i = 0; i < 4u; i++)
-                if (lo + i <= 8u) smem += (size_t)(32u << (lo + i)) * 4u;
-        } else {
-            smem += (size_t)(32u << p.hdr_bits) * 4u;
+        {   // ~7 CTAs (streams) per SM at the benchmark's 1024 streams: keep the CTA at or under 28 KB where possible
+            const int fb = p.vbr ? 0 : (int)p.hdr_bits;
+            const size_t e = enc_lut_entries(fb, p.base), other = smem + 256u + (p.vbr ? (size_t)enc_vbr_scratch_bytes(p) + 16u : 0u);
+            if (!p.vbr) lut_mode = enc_lut_mode_cbr(fb);
+            else if (other + e * 128u <= 28u * 1024u) lut_mode = kEncLut32;
+            else if (other + e * 64u <= 28u * 1024u) lut_mode = kEncLut16;
+            else lut_mode = kEncLutGlobal;
+            if (lut_mode != kEncLutGlobal) smem += e * (lut_mode == kEncLut32 ? 128u : 64u);
         }
         smem += 64u * 4u;  // reciprocals [slot][16]
     }
     EncParams pp = p;
     pp.vbr_smem_off = 0;
+    pp.lut_mode = (uint32_t)lut_mode;
     if (p.vbr) {  // keep the per-chunk VBR scratch in shared memory when it is small (stereo: 8.7 KB)
         const uint64_t sc = enc_vbr_scratch_bytes(p);
         if (sc <= 40u * 1024u && smem + sc + 16u <= 200u * 1024u) {

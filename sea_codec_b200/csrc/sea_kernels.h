@@ -67,6 +67,7 @@ struct EncParams {
     uint32_t raw_chunk_mode;   // 1: write only the chunk at out_off, no file header (make_chunk seam)
     uint32_t n_streams;
     uint32_t vbr_smem_off;     // != 0: the VBR scratch (ranks, sort keys, sizes) lives in shared memory at this offset
+    uint32_t lut_mode;         // VBR fast pass: where the dequant rows live (encode_kernels.cu kEncLut*); set by the launcher
 };
 
 // Persistent per-channel encoder state (EncoderBase.lms + prev_scalefactor, encoder_base.rs:15-19): 9 int32 per channel
