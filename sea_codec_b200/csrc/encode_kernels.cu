@@ -300,7 +300,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
             unsigned long long rank = 0;
             const int16_t *xs = xbuf + grp * F;
-            uint8_t *cbuf = codes + threadIdx.x;
+            uint8_t *cbuf = codes + warp * (F * 32u) + lane;  // [frame][lane] per warp: constant stride, immediate offsets when unrolled
             // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
             auto trial = [&](auto narrow_tag, auto lut_tag) {
                 constexpr bool kNarrow = decltype(narrow_tag)::value;
@@ -315,10 +315,10 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
                     const int32_t n = (int32_t)(((int64_t)r * (int64_t)recip + 32768) >> 16);
                     const uint32_t an = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;
-                    uint32_t k = an >> 1;
-                    k = k < kmax ? k : kmax;
-                    if ((FB > 0 ? (uint32_t)FB : size) == 2u) k = an >= 3u ? 1u : 0u;
-                    const uint32_t code = 2u * k + ((uint32_t)r >> 31);
+                    // qt.rs:9-31 closed form: 2*min(an >> 1, kmax) == min(an, 2*kmax + 1) & ~1 (size 2: magnitude index is an >= 3)
+                    uint32_t k2 = (an < 2u * kmax + 1u ? an : 2u * kmax + 1u) & ~1u;
+                    if ((FB > 0 ? (uint32_t)FB : size) == 2u) k2 = an >= 3u ? 2u : 0u;
+                    const uint32_t code = k2 + ((uint32_t)r >> 31);
                     const int32_t d = kMode == kEncLutGlobal ? __ldg(row + code) : row[code << (kMode == kEncLut32 ? 5 : 4)];
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
                     const int32_t y = clamp_i16(v);
@@ -328,7 +328,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     for (int i = 0; i < 4; i++) w[i] += delta * sg[i];
                     h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = y;
                     sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (v >> 31) | 1;  // the clamp keeps the sign
-                    cbuf[(size_t)f * T] = (uint8_t)code;
+                    cbuf[f * 32u] = (uint8_t)code;
                 }
             };
             const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
@@ -376,10 +376,10 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     blockbit = blk * F * rowbits;
                     prefix = c * size;
                 }
-                const uint8_t *wbuf = codes + (threadIdx.x - lane + g_lane);
+                const uint8_t *wbuf = codes + warp * (F * 32u) + g_lane;
                 __syncwarp(__activemask());  // the winner's codes were written by another lane
                 for (uint32_t f = sf; f < nf; f += lpc)
-                    put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[(size_t)f * T]);
+                    put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[f * 32u]);
             }
             __syncwarp();  // everybody is done with this block's samples and codes
             if (pre) {

@@ -73,8 +73,12 @@ SEA_HD uint64_t rank_step(uint64_t rank, int32_t err, const int32_t w[4])
                          (uint64_t)((int64_t)w[3] * w[3]);
     rank += (uint64_t)((int64_t)err * (int64_t)err);
     if (NARROW) {
+#if defined(__CUDA_ARCH__)
+        const int32_t t = __viaddmax_s32((int32_t)(uint32_t)(sum >> 18), -0x8ff, 0);  // one VIADDMNMX
+#else
         int32_t t = (int32_t)(uint32_t)(sum >> 18) - 0x8ff;
         t = t > 0 ? t : 0;
+#endif
         return rank + (uint64_t)(uint32_t)t * (uint64_t)(uint32_t)t;
     }
     const int64_t p = ((int64_t)sum >> 18) - 0x8ff;
