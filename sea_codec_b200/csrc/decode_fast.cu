@@ -22,7 +22,7 @@
 #include "sea_kernels.h"
 
 #ifndef SEA_DEC_WARPS
-#define SEA_DEC_WARPS 16
+#define SEA_DEC_WARPS 12
 #endif
 
 namespace sea {

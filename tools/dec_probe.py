@@ -19,7 +19,8 @@ elif os.environ.get("PROBE_STREAM") == "torch":
     _ts = torch.cuda.Stream()
     ctx.set_stream(_ts.cuda_stream)
 frames = int(sys.argv[6]) if len(sys.argv) > 6 else secs * 44100  # argv[6]: exact frame count (e.g. a multiple of 5120: no partial chunk)
-st = S.EncoderSettings(residual_bits=bits)
+vbr = bool(int(os.environ.get("PROBE_VBR", "0")))
+st = S.EncoderSettings(residual_bits=bits, vbr=vbr)
 u = min(n, 16)
 pcm = synth.gen_batch_torch(u, frames, ch, 44100, dev)
 bound = ctx.encode_bound(frames, ch, st)
@@ -38,7 +39,10 @@ for i in range(iters):
 ok = bool(torch.equal(out.view(n, spp)[:u].view(u, frames, ch), pcm.view(u, frames, ch)) is False)  # lossy codec: only replica equality below
 rep = torch.equal(out.view(n, spp)[n - 1], out.view(n, spp)[(n - 1) % u])
 best = min(ms[1:]) if len(ms) > 1 else ms[0]
-print("all iterations (ms):", " ".join(f"{m:.3f}" for m in ms))
+if os.environ.get("PROBE_VERBOSE"):
+    print("all iterations (ms):", " ".join(f"{m:.3f}" for m in ms))
+sustained = float(np.mean(ms[len(ms) // 2:])) if len(ms) >= 20 else None
 alg = n * bound + 2 * n * spp
-print(f"lib={os.path.basename(os.environ.get('SEA_B200_LIB', 'default'))} n={n} ch={ch} bits={bits}: best {best:.3f} ms  "
-      f"{n*spp/best/1e3:.0f} Msamples/s  {alg/best/1e6:.0f} GB/s ({alg/best/1e6/6550.4*100:.1f}% of HBM peak) replicas_equal={rep}")
+print(f"lib={os.path.basename(os.environ.get('SEA_B200_LIB', 'default'))} n={n} ch={ch} bits={bits}{' vbr' if vbr else ''}: best {best:.3f} ms  "
+      f"{n*spp/best/1e3:.0f} Msamples/s  {alg/best/1e6:.0f} GB/s ({alg/best/1e6/6550.4*100:.1f}% of HBM peak) replicas_equal={rep}"
+      + (f"  sustained {sustained:.3f} ms ({alg/sustained/1e6/6550.4*100:.1f}%)" if sustained else ""))
