@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(128) decode_generic_kernel(const uint8_t *__re
             w[i] = (int16_t)(l[8 + 2 * i] | (l[8 + 2 * i + 1] << 8));
         }
     }
+    int32_t sg[4];
+    lms_signs(sg, h);
     const uint32_t nblk = div_ceil_u32(frames, F), items = nblk * C;
     const uint32_t sf_sec = 4u + 16u * C;
     const uint32_t vbr_sec = sf_sec + div_ceil_u32(items * s, 8u);
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(128) decode_generic_kernel(const uint8_t *__re
             const int32_t y = clamp_i16((int32_t)((uint32_t)lms_predict(w, h) + (uint32_t)d));  // decoder.rs:38-45
             *out = (int16_t)y;
             out += C;
-            lms_update(w, h, y, d);
+            lms_update_sg(w, h, sg, y, d);
         }
     }
 }
@@ -210,6 +212,8 @@ decode_staged_kernel(const uint8_t *__restrict__ sea, uint64_t sea_len, int16_t 
             out = pcm + st.pcm_off + (uint64_t)k * p.N * C;
         }
     }
+    int32_t sg[4];
+    lms_signs(sg, h);
     if (c == 0) {
         row_out[j] = reinterpret_cast<uint64_t>(out);
         row_in[j] = res_off;
@@ -312,7 +316,7 @@ decode_staged_kernel(const uint8_t *__restrict__ sea, uint64_t sea_len, int16_t 
                 const int32_t d = lrow[code];
                 const int32_t y = clamp_i16((int32_t)((uint32_t)lms_predict(w, h) + (uint32_t)d));
                 my_out[(f + i) * C] = (int16_t)y;
-                lms_update(w, h, y, d);
+                lms_update_sg(w, h, sg, y, d);
             }
             rowpos += (uint64_t)n * rowbits;
             blk_left -= n;

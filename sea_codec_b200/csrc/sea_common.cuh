@@ -53,6 +53,20 @@ SEA_HD void lms_update(int32_t w[4], int32_t h[4], int32_t y, int32_t d)
     h[3] = y;
 }
 
+// The same update with the history signs carried in registers (sg[i] = h[i] < 0 ? -1 : +1, zero counts as +): the per-tap
+// shift+or of lms_update becomes one per sample.  Callers initialise sg from h once per chunk.
+SEA_HD void lms_signs(int32_t sg[4], const int32_t h[4])
+{
+    for (int i = 0; i < 4; i++) sg[i] = (h[i] >> 31) | 1;
+}
+SEA_HD void lms_update_sg(int32_t w[4], int32_t h[4], int32_t sg[4], int32_t y, int32_t d)
+{
+    const int32_t delta = d >> 4;
+    for (int i = 0; i < 4; i++) w[i] = (int32_t)((uint32_t)w[i] + (uint32_t)(delta * sg[i]));
+    h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = y;
+    sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (y >> 31) | 1;
+}
+
 // lms.rs:53-62 -- max(0, (sum w^2 >> 18) - 0x8ff)^2, wrapping u64 like the release build.
 SEA_HD uint64_t lms_penalty(const int32_t w[4])
 {
