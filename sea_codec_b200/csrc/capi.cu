@@ -213,7 +213,9 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     // Descriptor table on the device: [0, n) every chunk of every stream; when the unrolled kernel applies, [n, 2n) the full
     // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
     std::vector<DecStream> table(job.streams);
-    bool unrolled = fast && decode_unrolled_supported(fp) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
+    const bool use_vbr = fast && decode_vbr_supported(fp);  // the VBR twin of the unrolled kernel: same split, same constraints
+    bool unrolled = fast && (use_vbr || decode_unrolled_supported(fp)) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
+    const uint64_t tail_slack = use_vbr ? 320u : 128u;     // bytes both kernels may read past the last chunk they are given
     uint64_t chains_a = 0, chains_b = 0;
     if (unrolled) {
         table.resize((size_t)3 * n_streams);
@@ -221,7 +223,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
             const DecStream &d = job.streams[i];
             if (d.pcm_off % 16) unrolled = false;  // 256-bit stores need 32-byte aligned rows
             uint64_t n_full = std::min<uint64_t>(d.total_frames / fp.N, d.n_chunks);
-            while (n_full > 0 && d.data_off + n_full * fp.chunk_size + 128 > sea_len) n_full--;
+            while (n_full > 0 && d.data_off + n_full * fp.chunk_size + tail_slack > sea_len) n_full--;
             DecStream a = d, b = d;
             a.n_chunks = (uint32_t)n_full;
             a.total_frames = (uint32_t)(n_full * fp.N);
@@ -260,7 +262,8 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
                 ctx->launches++;
                 CU(cudaEventRecord(L.ev_join, L.side));
             }
-            CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
+            if (use_vbr) CU(launch_decode_vbr(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
+            else CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
             ctx->launches++;
             if (fb.total_chunks) CU(cudaStreamWaitEvent(L.stream, L.ev_join, 0));
         } else {

@@ -1,0 +1,293 @@
+// decode_vbr.cu -- the throughput decode kernel for uniform VBR batches: decode_vbr_kernel<C> (1 or 2 channels,
+// scale_factor_frames = 20, scale_factor_bits = 4, full chunks; everything else stays with decode_staged_kernel).
+//
+// Same mapping as decode_unrolled_kernel (decode_fast.cu): one CHUNK per lane, all C channels of it in one thread, PCM leaves
+// the registers as 256-bit stores, LMS signs carried in registers, I2IP pack-saturate clamp.  What VBR changes
+// (chunk.rs:126-139, codec/decoder.rs:52-86): every (block, channel) has its own residual size, so field positions are run-time
+// values and every lane walks its bit stream at its own pace:
+//   * residual bytes are staged per lane into a 128-byte ring (16-byte cp.async granules, topped up once per block, one block
+//     ahead of their use);
+//   * a 32-bit window is re-read from the ring every K frames (K * frame bits <= 32), so inside those frames a field is one
+//     shift by a per-block register and the window advances with one shift;
+//   * the dequant rows of the four sizes a chunk can use (header size - 1 .. + 2) sit in shared memory as uploaded
+//     ([size][sf][code], 4-byte stride).
+#include "sea_kernels.h"
+
+namespace sea {
+
+namespace {
+
+__device__ __forceinline__ void report_v(int *err, int code) { atomicCAS(err, 0, code); }
+__device__ __forceinline__ uint32_t smem_u32v(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_if(bool pred, uint32_t dst, const void *src)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}" ::"r"((int)pred), "r"(dst), "l"(src)
+        : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds_s32v(uint32_t addr)
+{
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void st_global_256v(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t find_stream_v(const DecStream *streams, uint32_t n_streams, uint64_t chain)
+{
+    uint32_t lo = 0, hi = n_streams;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)streams[mid].chain_begin <= chain) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int C>
+struct VCfg {
+    static constexpr int F = 20;
+    static constexpr int kRows = 32;                 // chunks per warp: one per lane
+    static constexpr int kBlkPerBody = 4 / C;        // the looped body is 80 samples: 2 stereo blocks / 4 mono blocks
+    static constexpr int kBodyFrames = kBlkPerBody * F;
+    static constexpr int kBodiesPerRound = 4;        // a round = 16 scale factors (8 bytes) and 16 size codes (4 bytes)
+    static constexpr int kRoundFrames = kBodiesPerRound * kBodyFrames;  // 160 stereo / 320 mono
+    static constexpr int K = 4 / C;                  // frames per window re-read: K * C * 8 bits <= 32
+    static constexpr int kOutFrames = 16 / C;        // frames per 32-byte store
+    static constexpr int kRingWords = 32;            // 128-byte ring per lane
+    static constexpr int kPitch = 144;               // ring + one pad granule: consecutive lanes start 4 banks apart
+    static constexpr int kWarpBytes = kRows * kPitch + 64;  // rows 8j.. skewed by j granules
+    static constexpr int kWarps = 12;
+};
+
+}  // namespace
+
+template <int C>
+__global__ void __launch_bounds__(VCfg<C>::kWarps * 32, 1)
+decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams, DecFastParams p,
+                  const int32_t *__restrict__ tab, int *err)
+{
+    using Cfg = VCfg<C>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t s = 4;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t hb = p.b;                                    // chunk-header residual size
+    const uint32_t lo_size = hb > 1u ? hb - 1u : 1u, hi_size = hb + 2u < 8u ? hb + 2u : 8u;
+
+    // ---- dequant rows of sizes lo_size..hi_size, contiguous in the uploaded table (sea_common.cuh: tab_dqt_off)
+    const uint32_t lut_words = tab_dqt_off(s, hi_size + 1u) - tab_dqt_off(s, lo_size);
+    int32_t *lut = reinterpret_cast<int32_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
+    for (uint32_t i = threadIdx.x; i < lut_words; i += blockDim.x) lut[i] = tab[tab_dqt_off(s, lo_size) + i];
+    __syncthreads();
+    const uint32_t lut_sh = smem_u32v(lut);
+
+    uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + lane;  // global chunk index
+    const bool valid = g < p.total_chunks;
+    if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
+
+    const DecStream st = streams[find_stream_v(streams, p.n_streams, g * C)];
+    const uint32_t k = (uint32_t)(g - st.chain_begin / C);
+    const uint64_t ck_off = st.data_off + (uint64_t)k * p.chunk_size;
+    const uint8_t *ck = sea + ck_off;
+    {
+        const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
+        if (word != p.hdr_word) report_v(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
+    }
+    int32_t w[C][4], h[C][4], sg[C][4];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const uint8_t *l = ck + 4u + 16u * c;  // lms.rs:80-94
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            h[c][i] = (int16_t)(l[2 * i] | (l[2 * i + 1] << 8));
+            w[c][i] = (int16_t)(l[8 + 2 * i] | (l[8 + 2 * i + 1] << 8));
+            sg[c][i] = (h[c][i] >> 31) | 1;
+        }
+    }
+    const uint32_t items = (p.N / Cfg::F) * C;
+    const uint64_t sf_off = ck_off + 4u + 16u * C;              // chunk.rs:108-113
+    const uint64_t vbr_off = sf_off + items / 2u;               // s == 4: two items per byte (items is even: N/F even)
+    const uint64_t res_off = vbr_off + items / 4u;              // chunk.rs:126-139: 2 bits per item
+    const uint64_t res_bits_avail = ((uint64_t)p.chunk_size - (res_off - ck_off)) * 8u;
+    uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
+
+    // ---- per-lane ring of residual bytes.  Word w of the 16-byte aligned stream sits at ring word (w & 31).
+    const uint64_t a0 = res_off & ~(uint64_t)15;                 // aligned start of what this lane stages
+    const uint8_t *src0 = sea + a0;
+    const uint32_t ring_sh = smem_u32v(smem + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
+    uint32_t fetched = 0;                                        // granules issued so far
+    uint32_t posg = (uint32_t)(res_off - a0) * 8u;               // bit position of the next field, from a0
+    const uint32_t pos_begin = posg;
+#pragma unroll
+    for (int t = 0; t < 8; t++) cp_async16_if(true, ring_sh + t * 16, src0 + t * 16);
+    fetched = 8;
+    cp_commit();
+    cp_commit();  // keeps the "all but the newest group" wait of the first block meaningful
+    cp_wait0();
+
+    // ---- scale factors (8 bytes per round) and size codes (4 bytes per round): aligned words one round ahead, realigned and
+    // byte-swapped by PRMT (per-lane byte phase), rotated at the END of a round so that nothing waits for the loads
+    const uint32_t *sfw = reinterpret_cast<const uint32_t *>(sea + (sf_off & ~(uint64_t)3));
+    const uint32_t *szw = reinterpret_cast<const uint32_t *>(sea + (vbr_off & ~(uint64_t)3));
+    const uint32_t sf_sel = 0x0123u + ((uint32_t)sf_off & 3u) * 0x1111u, sz_sel = 0x0123u + ((uint32_t)vbr_off & 3u) * 0x1111u;
+    uint32_t sf_a = __ldg(sfw), sf_b = __ldg(sfw + 1), sf_c = __ldg(sfw + 2), sf_n0 = 0, sf_n1 = 0;
+    uint32_t sz_a = __ldg(szw), sz_b = __ldg(szw + 1), sz_n = 0;
+
+    const uint32_t n_rounds = p.N / Cfg::kRoundFrames;
+    bool bad = false;
+
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        // big-endian: the round's 16 scale-factor nibbles (first in the top nibble of sfr0) and 16 two-bit size codes (szr)
+        const uint32_t sfr0 = __byte_perm(sf_a, sf_b, sf_sel), sfr1 = __byte_perm(sf_b, sf_c, sf_sel);
+        const uint32_t szr = __byte_perm(sz_a, sz_b, sz_sel);
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_n0) : "l"(sfw + 2 * r + 3));  // both stay inside the chunk
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_n1) : "l"(sfw + 2 * r + 4));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sz_n) : "l"(szw + r + 2));
+
+#pragma unroll 1
+        for (uint32_t bd = 0; bd < (uint32_t)Cfg::kBodiesPerRound; bd++) {
+            // items of this body: 4 (block, channel) pairs -> 4 nibbles of sfr, 4 size codes of szr
+            const uint32_t sf4 = ((bd & 2u) ? sfr1 : sfr0) >> (16u * (1u - (bd & 1u)));  // low 16 bits: this body's nibbles
+            const uint32_t sz4 = szr >> (24u - 8u * bd);                                    // low 8 bits: this body's codes
+            uint8_t *ob = out + ((size_t)(r * Cfg::kBodiesPerRound + bd)) * (Cfg::kBodyFrames * C * 2);
+            uint32_t ow[8];
+            int32_t y_even = 0;
+#pragma unroll
+            for (int q = 0; q < Cfg::kBlkPerBody; q++) {
+                // ---- top the ring up (<= 3 granules: a block consumes at most 40 bytes), then wait for everything but that
+                {
+                    const uint32_t wq = posg >> 5;
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        const bool room = fetched * 4u + 4u <= wq + (uint32_t)Cfg::kRingWords;
+                        cp_async16_if(room, ring_sh + (fetched & 7u) * 16u, src0 + (size_t)fetched * 16u);
+                        fetched += room ? 1u : 0u;
+                    }
+                    cp_commit();
+                    cp_wait1();
+                }
+                uint32_t size[C], rowbase[C];
+                uint32_t st_bits = 0;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const int item = q * C + c;
+                    const uint32_t sfv = (sf4 >> (12 - 4 * item)) & 15u;
+                    const uint32_t sz = ((sz4 >> (6 - 2 * item)) & 3u) + hb - 1u;  // chunk.rs:136-138
+                    bad |= sz < 1u || sz > 8u;
+                    size[c] = sz < lo_size ? lo_size : (sz > hi_size ? hi_size : sz);  // keeps the look-up inside the table
+                    rowbase[c] = lut_sh + ((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) * 4u;
+                    st_bits += size[c];
+                }
+                const uint32_t sh_frame = 32u - st_bits;      // frame field (both channels) -> low bits
+                const uint32_t m_last = (1u << size[C - 1]) - 1u;
+#pragma unroll
+                for (int i0 = 0; i0 < Cfg::F; i0 += Cfg::K) {
+                    // 32 valid bits of the stream at posg (MSB first): two ring words, byte-swapped, funnel-shifted
+                    const uint32_t wi = posg >> 5;
+                    const uint32_t r0 = lds_u32(ring_sh + (wi & 31u) * 4u), r1 = lds_u32(ring_sh + ((wi + 1u) & 31u) * 4u);
+                    uint32_t win = __funnelshift_l(__byte_perm(r1, 0, 0x0123), __byte_perm(r0, 0, 0x0123), posg & 31u);
+                    posg += (uint32_t)Cfg::K * st_bits;
+#pragma unroll
+                    for (int kk = 0; kk < Cfg::K; kk++) {
+                        const int fi = q * Cfg::F + i0 + kk;   // frame inside the body
+                        const uint32_t x = win >> sh_frame;
+                        win <<= st_bits;
+                        int32_t y[C], d[C];
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const uint32_t code = (c == C - 1) ? (x & m_last) : (x >> size[C - 1]);
+                            d[c] = lds_s32v(rowbase[c] + code * 4u);
+                            const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
+                                                 (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
+                            y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:74, before the clamp
+                        }
+                        uint32_t packed = 0;
+                        int32_t sgn[C];
+#pragma unroll
+                        for (int c = 0; c < C; c++) sgn[c] = (y[c] >> 31) | 1;  // the clamp keeps the sign
+                        if (C == 2) {
+                            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[C - 1]), "r"(y[0]));
+                            y[0] = (int32_t)(int16_t)(packed & 0xffffu);
+                            y[C - 1] = (int32_t)packed >> 16;
+                        } else if ((fi & 1) == 0) {
+                            y[0] = clamp_i16(y[0]);
+                            y_even = y[0];
+                        } else {
+                            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[0]), "r"(y_even));
+                            y[0] = (int32_t)packed >> 16;
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const int32_t delta = d[c] >> 4;  // lms.rs:43-51
+                            w[c][0] += delta * sg[c][0];
+                            w[c][1] += delta * sg[c][1];
+                            w[c][2] += delta * sg[c][2];
+                            w[c][3] += delta * sg[c][3];
+                            h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
+                            sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
+                        }
+                        if (C == 2) ow[fi & 7] = packed;
+                        else if (fi & 1) ow[(fi >> 1) & 7] = packed;
+                        if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256v(ob + (fi / Cfg::kOutFrames) * 32, ow);
+                    }
+                }
+            }
+        }
+        sf_a = sf_c;
+        sf_b = sf_n0;
+        sf_c = sf_n1;
+        sz_a = sz_b;
+        sz_b = sz_n;
+    }
+    // a size outside 1..8 panics in the reference (common.rs:34); more residual bits than the chunk holds is a slice error
+    if (bad || (uint64_t)(posg - pos_begin) > res_bits_avail) report_v(err, kDevFallback);
+}
+
+bool decode_vbr_supported(const DecFastParams &p)
+{
+    if (p.channels != 1 && p.channels != 2) return false;
+    if ((p.hdr_word & 0xffu) != 2u) return false;  // VBR chunks only
+    if (p.F != 20 || p.s != 4 || p.b < 1 || p.b > 8) return false;
+    const uint32_t round_frames = 640u / p.channels / 2u * 1u;  // VCfg::kRoundFrames: 160 stereo, 320 mono
+    if (p.N == 0 || p.N % round_frames != 0) return false;
+    return true;
+}
+
+template <int C>
+static cudaError_t launch_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, const int32_t *tab,
+                              int *d_err, cudaStream_t stream)
+{
+    using Cfg = VCfg<C>;
+    const uint32_t lo = p.b > 1u ? p.b - 1u : 1u, hi = p.b + 2u < 8u ? p.b + 2u : 8u;
+    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + (size_t)(tab_dqt_off(4, hi + 1u) - tab_dqt_off(4, lo)) * 4u;
+    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
+    const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
+    decode_vbr_kernel<C><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
+                              int *d_err, cudaStream_t stream)
+{
+    if (p.total_chunks == 0) return cudaSuccess;
+    const int32_t *tab = tabs.by_s[p.s];
+    return p.channels == 1 ? launch_vbr<1>(d_sea, d_pcm, d_streams, p, tab, d_err, stream)
+                           : launch_vbr<2>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+}
+
+}  // namespace sea

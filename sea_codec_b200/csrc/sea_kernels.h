@@ -47,6 +47,12 @@ bool decode_unrolled_supported(const DecFastParams &p);
 cudaError_t launch_decode_unrolled(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
                                    DevTables tabs, int *d_err, cudaStream_t stream);
 
+// VBR twin (decode_vbr.cu): VBR chunks, 1 or 2 channels, scale_factor_bits = 4, scale_factor_frames = 20, FULL chunks only, the same
+// alignment rules, >= 320 readable bytes after every chunk it is given.
+bool decode_vbr_supported(const DecFastParams &p);
+cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
+                              int *d_err, cudaStream_t stream);
+
 // ---- encode ------------------------------------------------------------------------------------------------
 struct EncStream {
     uint64_t pcm_off;   // sample offset of the stream's PCM

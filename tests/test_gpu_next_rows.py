@@ -216,3 +216,39 @@ def test_randomised_settings_against_oracle(ctx, oracle):
         assert np.array_equal(dec.samples, oracle.sea_decode(ref).samples), (case, ch, frames, kw)
         checked += 1
     assert checked >= 30, (checked, rejected)
+
+
+@pytest.mark.parametrize("channels,bits", [(2, 1.5), (2, 3.0), (2, 5.0), (2, 6.0), (2, 7.3), (1, 2.0), (1, 4.5), (1, 7.0)])
+def test_vbr_uniform_batch_throughput_kernel(ctx, oracle, channels, bits):
+    """decode_vbr_kernel (lane per chunk, run-time field widths): uniform VBR batches with several full chunks per stream and a
+    ragged tail (which the staged kernel takes) must match the oracle for every header size 1..7 and both channel counts."""
+    files, refs = [], []
+    for i in range(9):
+        frames = 5120 * (2 + i % 3) + (i * 733) % 5120
+        kind = i % 3
+        if kind == 0:
+            pcm = synth.gen_stream(300 + i, frames, channels, 44100)
+        elif kind == 1:  # loud: exercises the clamp in the pack-saturate path
+            t = np.arange(frames * channels)
+            pcm = np.clip(36000 * np.sin(t * 0.03) + 2000 * np.cos(t * 1.7), -32768, 32767).astype(np.int16)
+        else:  # quiet: ties and small sizes
+            pcm = (np.random.default_rng(i).integers(-300, 301, frames * channels)).astype(np.int16)
+        enc = oracle.sea_encode(pcm, 44100, channels, oracle.make_settings(bits, True))
+        files.append(enc)
+        refs.append(oracle.sea_decode(enc).samples)
+    for o, r in zip(ctx.decode_batch(files), refs):
+        assert np.array_equal(o.samples, r)
+
+
+def test_vbr_corrupt_size_codes_match_the_generic_verdict(ctx, oracle):
+    """A chunk whose size codes ask for more residual bits than it holds is a slice error in the reference (chunk.rs:190-196): the
+    throughput kernel must notice and hand the batch to the generic path, which reports Domain -- not decode garbage."""
+    pcm = synth.gen_stream(77, 5120 * 3, 2, 44100)
+    enc = bytearray(oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(3.0, True)))
+    hdr = S.parse_header(bytes(enc))
+    vbr_sec = 22 + hdr.chunk_size + 4 + 32 + 256          # second chunk: header, LMS, 512 scale-factor nibbles
+    for i in range(128):
+        enc[vbr_sec + i] = 0xFF                            # every block asks for header size + 2
+    with pytest.raises(api.SeaError) as e:
+        ctx.decode_batch([bytes(enc)] * 4)
+    assert e.value.code == api.ERR_DOMAIN
