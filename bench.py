@@ -297,6 +297,34 @@ def main():
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_msamples_per_s": samples_per_step / (k_ms * 1e-3) / 1e6}
 
+    # ---- the VBR twin of the headline (decode_vbr_kernel): same stream shape, VBR 3.0, a quarter of the streams
+    vbr_dec = None
+    if not args.skip_encode:
+        st_v = S.EncoderSettings(residual_bits=3.0, vbr=True)
+        nv = max(unique, n // 4)
+        bound_v = ctx.encode_bound(frames, CHANNELS, st_v)
+        stride_v = (bound_v + 15) // 16 * 16
+        sea_vu = torch.zeros(unique * stride_v, dtype=torch.uint8, device=dev)
+        lens_vu = ctx.encode_batch_device(pcm_u.data_ptr(), np.arange(unique) * frames * CHANNELS, np.full(unique, frames), RATE, CHANNELS,
+                                          st_v, sea_vu.data_ptr(), np.arange(unique) * stride_v)
+        sea_v = sea_vu.view(unique, stride_v).repeat(nv // unique, 1).contiguous().view(-1)
+        hdr_v = np.tile(sea_vu.view(unique, stride_v)[:, :22].cpu().numpy(), (nv // unique, 1))
+        len_v = np.tile(lens_vu, nv // unique)
+        ks = []
+        for _ in range(2 + max(3, min(args.steps, 10))):
+            got_v = ctx.decode_batch_device(sea_v.data_ptr(), np.arange(nv, dtype=np.uint64) * stride_v, len_v, hdr_v, pcm_out.data_ptr(),
+                                            pcm_off[:nv])
+            ks.append(ctx.last_kernel_ms)
+        assert np.all(got_v == spp)
+        ms_v = dist.max_over_ranks(float(np.mean(ks[2:])))
+        bytes_v = float(len_v.sum() + 2 * nv * spp)
+        vbr_dec = {"value": info.world * nv * spp / (ms_v * 1e-3) / 1e6, "unit": "Msamples/s", "streams_per_gpu": nv, "ms_per_step": ms_v,
+                   "roofline": {"bound": "hbm", "kernel": "decode_vbr_kernel<2>", "achieved": bytes_v / (ms_v * 1e-3) / 1e9,
+                                "peak": measured_peaks()[0]["hbm_gbs"], "unit": "GB/s",
+                                "frac": bytes_v / (ms_v * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}}
+        del sea_v, sea_vu
+        torch.cuda.empty_cache()
+
     # ---- e2e: the same decode through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
     ne = min(args.e2e_streams, n)
     h_sea = torch.empty(ne * stride, dtype=torch.uint8).pin_memory()
@@ -379,7 +407,7 @@ def main():
             "metric": "decode_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": info.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i32", "data": "synthetic", "config": workload_config(args, unique), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "encode": encode,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode_vbr3": vbr_dec, "encode": encode,
         }))
     ctx.close()
     dist.shutdown()

@@ -11,6 +11,8 @@
 //     shift by a per-block register and the window advances with one shift;
 //   * the dequant rows of the four sizes a chunk can use (header size - 1 .. + 2) sit in shared memory as uploaded
 //     ([size][sf][code], 4-byte stride).
+#include <stdlib.h>
+
 #include "sea_kernels.h"
 
 namespace sea {
@@ -75,7 +77,10 @@ struct VCfg {
 
 }  // namespace
 
-template <int C>
+// RS = log2 of the replication of every table entry (copy lane & (2^RS - 1) is the one a lane reads).  The dependent look-up is
+// the busiest shared-memory access (un-replicated ~2.5 wavefronts per load, LSU data pipe 83 %), yet RS = 3 measured slower than
+// RS = 0 (see launch_decode_vbr), so RS = 0 is what runs.
+template <int C, int RS>
 __global__ void __launch_bounds__(VCfg<C>::kWarps * 32, 1)
 decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams, DecFastParams p,
                   const int32_t *__restrict__ tab, int *err)
@@ -90,9 +95,9 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
     // ---- dequant rows of sizes lo_size..hi_size, contiguous in the uploaded table (sea_common.cuh: tab_dqt_off)
     const uint32_t lut_words = tab_dqt_off(s, hi_size + 1u) - tab_dqt_off(s, lo_size);
     int32_t *lut = reinterpret_cast<int32_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
-    for (uint32_t i = threadIdx.x; i < lut_words; i += blockDim.x) lut[i] = tab[tab_dqt_off(s, lo_size) + i];
+    for (uint32_t i = threadIdx.x; i < (lut_words << RS); i += blockDim.x) lut[i] = tab[tab_dqt_off(s, lo_size) + (i >> RS)];
     __syncthreads();
-    const uint32_t lut_sh = smem_u32v(lut);
+    const uint32_t lut_sh = smem_u32v(lut) + (lane & ((1u << RS) - 1u)) * 4u;
 
     uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + lane;  // global chunk index
     const bool valid = g < p.total_chunks;
@@ -188,7 +193,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
                     const uint32_t sz = ((sz4 >> (6 - 2 * item)) & 3u) + hb - 1u;  // chunk.rs:136-138
                     bad |= sz < 1u || sz > 8u;
                     size[c] = sz < lo_size ? lo_size : (sz > hi_size ? hi_size : sz);  // keeps the look-up inside the table
-                    rowbase[c] = lut_sh + ((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) * 4u;
+                    rowbase[c] = lut_sh + (((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) << (2 + RS));
                     st_bits += size[c];
                 }
                 const uint32_t sh_frame = 32u - st_bits;      // frame field (both channels) -> low bits
@@ -209,7 +214,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
 #pragma unroll
                         for (int c = 0; c < C; c++) {
                             const uint32_t code = (c == C - 1) ? (x & m_last) : (x >> size[C - 1]);
-                            d[c] = lds_s32v(rowbase[c] + code * 4u);
+                            d[c] = lds_s32v(rowbase[c] + (code << (2 + RS)));
                             const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                                  (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                             y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:74, before the clamp
@@ -266,18 +271,17 @@ bool decode_vbr_supported(const DecFastParams &p)
     return true;
 }
 
-template <int C>
+template <int C, int RS>
 static cudaError_t launch_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, const int32_t *tab,
-                              int *d_err, cudaStream_t stream)
+                              int *d_err, size_t lut_bytes, cudaStream_t stream)
 {
     using Cfg = VCfg<C>;
-    const uint32_t lo = p.b > 1u ? p.b - 1u : 1u, hi = p.b + 2u < 8u ? p.b + 2u : 8u;
-    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + (size_t)(tab_dqt_off(4, hi + 1u) - tab_dqt_off(4, lo)) * 4u;
-    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + (lut_bytes << RS);
+    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
     const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
-    decode_vbr_kernel<C><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    decode_vbr_kernel<C, RS><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
     return cudaGetLastError();
 }
 
@@ -286,8 +290,17 @@ cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStr
 {
     if (p.total_chunks == 0) return cudaSuccess;
     const int32_t *tab = tabs.by_s[p.s];
-    return p.channels == 1 ? launch_vbr<1>(d_sea, d_pcm, d_streams, p, tab, d_err, stream)
-                           : launch_vbr<2>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+    const uint32_t lo = p.b > 1u ? p.b - 1u : 1u, hi = p.b + 2u < 8u ? p.b + 2u : 8u;
+    const size_t lut_bytes = (size_t)(tab_dqt_off(4, hi + 1u) - tab_dqt_off(4, lo)) * 4u;
+    // Measured (1024 stereo VBR-3 streams): replicated 5.03 ms, plain 4.86 ms -- the plain table is the default;
+    // SEA_B200_VBR_REP=1 selects the replicated one for tuning runs.
+    const char *env = getenv("SEA_B200_VBR_REP");
+    const bool rep = env && env[0] == '1' && lut_bytes * 8u <= 48u * 1024u;
+    if (p.channels == 1)
+        return rep ? launch_vbr<1, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream)
+                   : launch_vbr<1, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);
+    return rep ? launch_vbr<2, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream)
+               : launch_vbr<2, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);
 }
 
 }  // namespace sea
