@@ -327,9 +327,16 @@ def main():
 
     # ---- e2e: the same decode through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
     ne = min(args.e2e_streams, n)
-    h_sea = torch.empty(ne * stride, dtype=torch.uint8).pin_memory()
+    while True:  # pinned host memory is a shared resource on a multi-GPU box: shrink the sample rather than fail
+        try:
+            h_sea = torch.empty(ne * stride, dtype=torch.uint8).pin_memory()
+            h_pcm = torch.empty(ne * spp, dtype=torch.int16).pin_memory()
+            break
+        except RuntimeError:
+            if ne <= unique:
+                raise
+            ne = max(unique, ne // 2 // unique * unique)
     h_sea.copy_(sea[: ne * stride])
-    h_pcm = torch.empty(ne * spp, dtype=torch.int16).pin_memory()
     torch.cuda.synchronize()
 
     def e2e_step():
