@@ -41,6 +41,25 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(index: int) -> None:
+    """Pins this rank's host threads (and so its first-touch pinned buffers) to the CPUs NVML reports as local to the GPU: the
+    host-buffer (e2e) path moves ~6.5 GB per step over PCIe, and with several ranks per box remote-node buffers share one
+    inter-socket link."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 def ncu_traffic(streams: int, seconds: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per launch, from the committed `ncu --set full` capture
     (profiles/r01_decode_traffic.json: bytes per stream of the 60 s config-4 shape); None when the shape differs."""
@@ -221,6 +240,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsea_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(info.local_rank)
+    bind_to_gpu_numa_node(info.local_rank)
     dev = torch.device("cuda", info.local_rank)
     ctx = S.Context(info.local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)

@@ -6,6 +6,7 @@
 //   sea::SeaEncoder<R, W>::encode_frame/finalize  src/encoder.rs:50-159   (R: size_t read(void*, size_t); W: void write(const void*, size_t))
 //   sea::SeaDecoder<R, W>::decode_frame           src/decoder.rs:22-72
 //   sea::sea_encode / sea::sea_decode             src/lib.rs:13-63
+//   additions: SeaEncoder::encode_frames(k), SeaDecoder::decode_frames(k) (k chunks per launch), sea::sea_decode_range
 // Errors: sea::SeaError carries the SeaError variant (common.rs:53-64) as the C-ABI status code.
 #pragma once
 #include <cstdint>
@@ -167,6 +168,35 @@ public:
         if (eof) state_ = Finished;
         return !eof;
     }
+    // Up to max_chunks encode_frame() steps in ONE launch (sea_b200_encoder_make_chunks): same bytes, same state machine.
+    bool encode_frames(size_t max_chunks)
+    {
+        if (state_ == Finished) throw SeaError(SEA_B200_ERR_ENCODER_CLOSED, "encode_frames after the stream ended");
+        const size_t fpc = settings_.frames_per_chunk, want = fpc * max_chunks;
+        size_t frames = want;
+        if (total_frames_ > 0) frames = std::min<size_t>(want, (size_t)total_frames_ - written_frames_);
+        std::vector<uint8_t> raw = detail::read_max_or_zero(reader_, frames * channels_ * 2);
+        if (raw.size() % (2 * (size_t)channels_) != 0) throw SeaError(SEA_B200_ERR_IO, "UnexpectedEof (encoder.rs:95-99)");
+        const size_t n = raw.size() / 2;
+        const bool eof = n == 0 || n < want * channels_;
+        if (n) {
+            std::vector<uint8_t> chunks(70000 * max_chunks);
+            uint64_t len = 0;
+            uint32_t n_chunks = 0;
+            ctx_.check(sea_b200_encoder_make_chunks(enc_, reinterpret_cast<const int16_t *>(raw.data()), n, chunks.data(), chunks.size(), &len,
+                                                    &n_chunks));
+            if (state_ == Start) {
+                std::vector<uint8_t> h;
+                detail::put_header(h, channels_, (uint16_t)sea_b200_encoder_chunk_size(enc_), settings_.frames_per_chunk, sample_rate_, total_frames_);
+                writer_.write(h.data(), h.size());
+                state_ = Writing;
+            }
+            writer_.write(chunks.data(), (size_t)len);
+            written_frames_ += (uint32_t)(n / channels_);
+        }
+        if (eof) state_ = Finished;
+        return !eof;
+    }
     void flush() {}
     void finalize() { state_ = Finished; }
 
@@ -205,6 +235,20 @@ public:
         std::vector<int16_t> pcm((size_t)header_.frames_per_chunk * header_.channels);
         uint64_t n = 0;
         ctx_.check(sea_b200_decoder_decode_chunk(dec_, encoded.data(), encoded.size(), remaining, pcm.data(), pcm.size(), &n));
+        frames_read_ += n / header_.channels;
+        writer_.write(pcm.data(), (size_t)n * 2);
+        return true;
+    }
+    // Up to max_chunks decode_frame() steps in one chunk-parallel launch (sea_b200_decoder_decode_chunks).
+    bool decode_frames(size_t max_chunks)
+    {
+        if (header_.total_frames != 0 && header_.total_frames <= frames_read_) return false;
+        const int64_t remaining = header_.total_frames > 0 ? (int64_t)(header_.total_frames - frames_read_) : -1;
+        std::vector<uint8_t> encoded = detail::read_max_or_zero(reader_, (size_t)header_.chunk_size * max_chunks);
+        if (encoded.empty()) return false;
+        std::vector<int16_t> pcm((size_t)header_.frames_per_chunk * header_.channels * max_chunks);
+        uint64_t n = 0;
+        ctx_.check(sea_b200_decoder_decode_chunks(dec_, ctx_.get(), encoded.data(), encoded.size(), remaining, pcm.data(), pcm.size(), &n));
         frames_read_ += n / header_.channels;
         writer_.write(pcm.data(), (size_t)n * 2);
         return true;
@@ -248,6 +292,22 @@ inline SeaDecodeInfo sea_decode(Context &ctx, const uint8_t *encoded, size_t len
     ctx.check(sea_b200_decode(ctx.get(), encoded, len, nullptr, 0, &n, &info.sample_rate, &info.channels));
     info.samples.resize(n ? n : 1);
     ctx.check(sea_b200_decode(ctx.get(), encoded, len, info.samples.data(), info.samples.size(), &n, &info.sample_rate, &info.channels));
+    info.samples.resize(n);
+    return info;
+}
+
+// Random access (README.md:125 "seeking"): frames [first_frame, first_frame + n_frames) of a complete file; only the covering
+// chunks are decoded.  skip_metadata = the format-compatible fix of file.rs:53-54.
+inline SeaDecodeInfo sea_decode_range(Context &ctx, const uint8_t *encoded, size_t len, uint64_t first_frame, uint64_t n_frames,
+                                      bool skip_metadata = false)
+{
+    SeaDecodeInfo info;
+    uint64_t n = 0;
+    const uint32_t flags = skip_metadata ? SEA_B200_RANGE_SKIP_METADATA : 0u;
+    ctx.check(sea_b200_decode_range(ctx.get(), encoded, len, first_frame, n_frames, flags, nullptr, 0, &n, &info.sample_rate, &info.channels));
+    info.samples.resize(n ? n : 1);
+    ctx.check(sea_b200_decode_range(ctx.get(), encoded, len, first_frame, n_frames, flags, info.samples.data(), info.samples.size(), &n,
+                                    &info.sample_rate, &info.channels));
     info.samples.resize(n);
     return info;
 }

@@ -53,6 +53,30 @@ int main(int argc, char **argv)
             fprintf(stderr, "one-shot decode differs from streaming decode\n");
             return 1;
         }
+        // the multi-chunk forms must give the same bytes / samples, and a range must equal the slice of the whole
+        sea::SliceReader rd3(raw.data(), raw.size());
+        sea::VecWriter wr3;
+        sea::SeaEncoder<sea::SliceReader, sea::VecWriter> enc3(ctx, (uint8_t)channels, rate, (uint32_t)(n / channels), st, rd3, wr3);
+        while (enc3.encode_frames(2)) {}
+        if (wr3.data != wr.data) {
+            fprintf(stderr, "encode_frames(2) differs from encode_frame()\n");
+            return 1;
+        }
+        sea::SliceReader rd4(wr.data.data(), wr.data.size());
+        sea::VecWriter pcm4;
+        sea::SeaDecoder<sea::SliceReader, sea::VecWriter> dec4(ctx, rd4, pcm4);
+        while (dec4.decode_frames(3)) {}
+        if (pcm4.data != pcm_out.data) {
+            fprintf(stderr, "decode_frames(3) differs from decode_frame()\n");
+            return 1;
+        }
+        const uint64_t first = 5000, count = 6000;
+        sea::SeaDecodeInfo part = sea::sea_decode_range(ctx, one.data(), one.size(), first, count);
+        if (part.samples.size() != count * channels ||
+            memcmp(part.samples.data(), info.samples.data() + first * channels, part.samples.size() * 2) != 0) {
+            fprintf(stderr, "sea_decode_range differs from the slice of the full decode\n");
+            return 1;
+        }
         printf("ok %zu %zu %zu\n", one.size(), wr.data.size(), pcm_out.data.size());
         return 0;
     } catch (const sea::SeaError &e) {
