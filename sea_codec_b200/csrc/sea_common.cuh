@@ -103,9 +103,12 @@ SEA_HD uint64_t rank_step(uint64_t rank, int32_t err, const int32_t w[4])
 SEA_HD bool weights_stay_narrow(const int32_t w[4], uint32_t F)
 {
     const int32_t lim = (1 << 23) - 1 - (int32_t)F * 1600;
-    bool ok = true;
-    for (int i = 0; i < 4; i++) ok = ok && w[i] < lim && w[i] > -lim;
-    return ok;
+    uint32_t m = 0;  // max |w[i]| (|INT_MIN| wraps to 2^31 as unsigned: still >= lim)
+    for (int i = 0; i < 4; i++) {
+        const uint32_t a = w[i] < 0 ? 0u - (uint32_t)w[i] : (uint32_t)w[i];
+        m = a > m ? a : m;
+    }
+    return m < (uint32_t)lim;
 }
 
 // encoder_base.rs:22-26 (sea_div) + :71-72 (clamp, SeaQuantTab lookup) as one closed form.
