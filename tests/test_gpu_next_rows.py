@@ -252,3 +252,60 @@ def test_vbr_corrupt_size_codes_match_the_generic_verdict(ctx, oracle):
     with pytest.raises(api.SeaError) as e:
         ctx.decode_batch([bytes(enc)] * 4)
     assert e.value.code == api.ERR_DOMAIN
+
+
+def test_corrupted_files_never_disagree_with_the_oracle(ctx, oracle):
+    """Seeded corruption sweep: random byte flips, truncations and header edits of CBR and VBR files.  Whatever the oracle says
+    (samples, or an error where the reference errors or panics) the GPU path must say too -- alone and as a uniform batch of
+    copies, which is what routes through the throughput kernels -- and no input may crash the device."""
+    rng = np.random.default_rng(777)
+    pcm = synth.gen_stream(9, 5120 * 3 + 1234, 2, 44100)
+    bases = [oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(3.0)),
+             oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(3.0, True)),
+             oracle.sea_encode(pcm[::2].copy(), 44100, 1, oracle.make_settings(5.0, True))]
+
+    def verdict(fn):
+        try:
+            return True, fn()
+        except (api.SeaError, oracle.OracleError):
+            return False, None
+
+    n_err = n_ok = 0
+    for case in range(90):
+        f = bytearray(bases[case % 3])
+        kind = (case // 3) % 5
+        if kind == 0:      # flips inside chunk payloads / chunk headers
+            for _ in range(int(rng.integers(1, 6))):
+                f[int(rng.integers(22, len(f)))] ^= int(rng.integers(1, 256))
+        elif kind == 1:    # truncation anywhere after the file header
+            f = f[: int(rng.integers(22, len(f)))]
+        elif kind == 2:    # total_frames edited (shorter, slightly longer, streaming 0)
+            tf = int.from_bytes(f[14:18], "little")
+            new = int(rng.choice([0, tf - 1, tf - 5120, tf + 1, tf + 5120, 1, 5120]))
+            f[14:18] = max(new, 0).to_bytes(4, "little")
+        elif kind == 3:    # chunk_size / frames_per_chunk edited
+            cs = int.from_bytes(f[6:8], "little")
+            if rng.integers(0, 2):
+                f[6:8] = int(max(16, cs + int(rng.integers(-40, 41)))).to_bytes(2, "little")
+            else:
+                f[8:10] = int(rng.choice([5100, 5120 - 20, 5140, 2560, 100])).to_bytes(2, "little")
+        else:              # chunk header fields of one chunk: type, sizes byte, scale_factor_frames
+            cs = int.from_bytes(f[6:8], "little")
+            k = int(rng.integers(0, 3))
+            off = 22 + k * cs + int(rng.integers(0, 3))
+            if off < len(f):
+                f[off] = int(rng.integers(0, 256))
+        blob = bytes(f)
+        ok_o, want = verdict(lambda: oracle.sea_decode(blob).samples)
+        ok_g, got = verdict(lambda: ctx.sea_decode(blob).samples)
+        assert ok_o == ok_g, (case, kind, ok_o, ok_g)
+        if ok_o:
+            assert np.array_equal(got, want), (case, kind)
+            n_ok += 1
+        else:
+            n_err += 1
+        ok_b, got_b = verdict(lambda: [d.samples for d in ctx.decode_batch([blob] * 3)])
+        assert ok_b == ok_o, (case, kind, "batch")
+        if ok_o:
+            assert all(np.array_equal(g, want) for g in got_b), (case, kind, "batch")
+    assert n_ok >= 10 and n_err >= 10, (n_ok, n_err)
