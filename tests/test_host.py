@@ -163,3 +163,23 @@ def test_lms_arithmetic_matches_definition():
         delta = d >> 4
         exp = [(int(w[i]) + (-delta if h[i] < 0 else delta) + 2**31) % 2**32 - 2**31 for i in range(4)]
         assert w2.tolist() == exp and h2.tolist() == [h[1], h[2], h[3], y]
+
+
+def test_c_headers_compile_as_c_and_cpp(tmp_path):
+    """include/sea_b200.h is a plain C header (C99 and C++17), sea_compat.h keeps the reference's C-level names
+    (wasm_api.rs:32-111, c/sea.h:189) and resolves them to exported symbols; sea_b200.hpp compiles on its own."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    c_src = tmp_path / "t.c"
+    c_src.write_text('#include "sea_compat.h"\n'
+                     "int use(uint8_t *e, uint32_t n, int16_t *o) { uint32_t r, c, f; return sea_decode(e, n, &r, &c, o, &f); }\n"
+                     "size_t enc(const int16_t *p, size_t n, uint8_t *o, size_t cap) { setup(); return wasm_sea_encode(p, n, 44100, 2, 3.0f, 0, o, cap); }\n")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + inc, "-c", str(c_src), "-o", str(tmp_path / "t.o")], check=True)
+    syms = subprocess.run(["nm", "-u", str(tmp_path / "t.o")], capture_output=True, text=True, check=True).stdout
+    L = S.lib()
+    for name in ("sea_b200_csea_decode", "sea_b200_wasm_sea_encode", "sea_b200_wasm_setup"):
+        assert name in syms and hasattr(L, name)
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "sea_b200.hpp"\nint main() { sea::EncoderSettings s; return s.frames_per_chunk == 5120 ? 0 : 1; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, str(cpp)], check=True)
