@@ -305,8 +305,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             auto trial = [&](auto narrow_tag, auto lut_tag) {
                 constexpr bool kNarrow = decltype(narrow_tag)::value;
                 constexpr int kMode = decltype(lut_tag)::value;
-#pragma unroll 4
-                for (uint32_t f = 0; f < nf; f++) {
+                auto step = [&](uint32_t f) {
                     const int32_t xv = xs[f];
                     // lms.rs:33-41 as a two-level sum (wrapping adds associate): the newest history value enters last
                     const uint32_t acc = ((uint32_t)w[0] * (uint32_t)h[0] + (uint32_t)w[1] * (uint32_t)h[1]) +
@@ -329,6 +328,14 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = y;
                     sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (v >> 31) | 1;  // the clamp keeps the sign
                     cbuf[f * 32u] = (uint8_t)code;
+                };
+                if (nf == 20u) {  // the default block: fully unrolled (immediate offsets, no loop control, penalties of one step
+                                  // scheduled into the table-load shadow of the next)
+#pragma unroll
+                    for (uint32_t f = 0; f < 20u; f++) step(f);
+                } else {
+#pragma unroll 4
+                    for (uint32_t f = 0; f < nf; f++) step(f);
                 }
             };
             const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
