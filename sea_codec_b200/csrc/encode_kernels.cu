@@ -18,18 +18,23 @@ namespace sea {
 __device__ __forceinline__ void enc_report(int *err, int code) { atomicCAS(err, 0, code); }
 
 // OR an n <= 8 bit field into the big-endian word view of the chunk at absolute bit position pos.
-__device__ __forceinline__ void put_bits(uint32_t *buf, uint32_t pos, uint32_t n, uint32_t value)
+// The image lives in shared memory: the OR goes out as red.shared on a 32-bit shared-window address (atomicOr on the generic
+// pointer made the compiler rebuild the window address -- S2UR SR_CgaCtaId, ULEA -- and branch around every call: 7 % of the
+// stall samples of the 1024-stream profile).
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t value)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
+}
+__device__ __forceinline__ void put_bits(uint32_t base, uint32_t pos, uint32_t n, uint32_t value)  // base: shared-window address
 {
     const uint32_t word = pos >> 5, off = pos & 31u;
-    if (off + n <= 32u) {
-        atomicOr(&buf[word], value << (32u - off - n));
-    } else {
-        const uint32_t spill = off + n - 32u;
-        atomicOr(&buf[word], value >> spill);
-        atomicOr(&buf[word + 1], value << (32u - spill));
-    }
+    // MSB-first field as a 64-bit big-endian pair: the second word is zero unless the field straddles (OR of 0 is harmless,
+    // and one unconditional pair of reductions is cheaper than a divergent branch)
+    const uint64_t v64 = (uint64_t)value << (64u - off - n);
+    red_or_shared(base + word * 4u, (uint32_t)(v64 >> 32));
+    if (off + n > 32u) red_or_shared(base + word * 4u + 4u, (uint32_t)v64);
 }
-__device__ __forceinline__ void put_byte(uint32_t *buf, uint32_t byte_off, uint32_t v) { put_bits(buf, byte_off * 8u, 8u, v & 0xffu); }
+__device__ __forceinline__ void put_byte(uint32_t base, uint32_t byte_off, uint32_t v) { put_bits(base, byte_off * 8u, 8u, v & 0xffu); }
 
 struct VbrScratch {
     unsigned long long *keys;  // ranks, then sort keys           [npow2]
@@ -71,7 +76,7 @@ __device__ __forceinline__ VbrScratch carve_scratch(uint8_t *base, const EncPara
 // per-(block, channel) sizes.
 __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p, const int16_t *__restrict__ x0, uint32_t frames,
                             const int32_t *__restrict__ tab, int32_t *st_w, int32_t *st_h, int32_t *st_prev, uint8_t *codes,
-                            uint32_t *chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs)
+                            uint32_t chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs)
 {
     const uint32_t C = p.channels, F = p.F, s = p.s, nsf = 1u << s;
     const uint32_t lpc = nsf < 32u ? nsf : 32u;  // lanes per chain group
@@ -234,7 +239,7 @@ struct FastLut {
 template <int FB>
 __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParams &p, const int16_t *__restrict__ x0, uint32_t frames,
                                  const int32_t *__restrict__ tab, int32_t *st_w, int32_t *st_h, int32_t *st_prev, uint8_t *codes,
-                                 uint32_t *chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs, const FastLut &fl,
+                                 uint32_t chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs, const FastLut &fl,
                                  int16_t *xbuf_all)
 {
     constexpr uint32_t s = 4, nsf = 16, lpc = 16, cpw = 2;
@@ -448,6 +453,7 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
 
     const uint32_t buf_words = (p.max_chunk_bytes + 3u) / 4u + 2u;
     uint32_t *chunk_buf = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t chunk_sh = (uint32_t)__cvta_generic_to_shared(chunk_buf);  // for the red.shared bit writes
     int32_t *st_w = reinterpret_cast<int32_t *>(chunk_buf + buf_words);
     int32_t *st_h = st_w + 4 * C;
     int32_t *st_prev = st_h + 4 * C;
@@ -531,29 +537,29 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
         const uint32_t res_sec_bit = vbr_sec_bit + (p.vbr ? div_ceil_u32(items * 2u, 8u) * 8u : 0u);
 
         if (tid == 0) {  // chunk.rs:215-226
-            put_byte(chunk_buf, 0, p.vbr ? 2u : 1u);
-            put_byte(chunk_buf, 1, (s << 4) | p.hdr_bits);
-            put_byte(chunk_buf, 2, F);
-            put_byte(chunk_buf, 3, 0x5Au);
+            put_byte(chunk_sh, 0, p.vbr ? 2u : 1u);
+            put_byte(chunk_sh, 1, (s << 4) | p.hdr_bits);
+            put_byte(chunk_sh, 2, F);
+            put_byte(chunk_sh, 3, 0x5Au);
         }
         for (uint32_t i = tid; i < 4 * C; i += T) {  // lms.rs:64-78: low 16 bits, history then weights, LE
             const uint32_t c = i >> 2, t = i & 3u;
             const uint32_t hv = (uint32_t)sv_h[i], wv = (uint32_t)sv_w[i];
             const uint32_t base_byte = 4u + 16u * c;
-            put_byte(chunk_buf, base_byte + 2u * t, hv);
-            put_byte(chunk_buf, base_byte + 2u * t + 1u, hv >> 8);
-            put_byte(chunk_buf, base_byte + 8u + 2u * t, wv);
-            put_byte(chunk_buf, base_byte + 8u + 2u * t + 1u, wv >> 8);
+            put_byte(chunk_sh, base_byte + 2u * t, hv);
+            put_byte(chunk_sh, base_byte + 2u * t + 1u, hv >> 8);
+            put_byte(chunk_sh, base_byte + 8u + 2u * t, wv);
+            put_byte(chunk_sh, base_byte + 8u + 2u * t + 1u, wv >> 8);
         }
 
         if (!p.vbr) {
-            if (FB >= 0) search_pass_fast<FB>(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
-            else search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (FB >= 0) search_pass_fast<FB>(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            else search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
             if (tid == 0) sh_res_bits = frames * C * p.hdr_bits;
         } else {
             // ---- analysis at base+1 bits (encoder_vbr.rs:139-171); restores lms only (trap T2)
-            if (FB >= 0) search_pass_fast<FB>(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
-            else search_pass(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (FB >= 0) search_pass_fast<FB>(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            else search_pass(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
             __syncthreads();
             for (uint32_t i = tid; i < 4 * C; i += T) {
                 st_w[i] = sv_w[i];
@@ -604,11 +610,11 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
                 sh_res_bits = acc;
             }
             for (uint32_t i = tid; i < items; i += T)  // chunk.rs:245-252 (release build masks to 2 bits)
-                put_bits(chunk_buf, vbr_sec_bit + 2u * i, 2u, ((uint32_t)vs.sizes[i] - p.hdr_bits + 1u) & 3u);
+                put_bits(chunk_sh, vbr_sec_bit + 2u * i, 2u, ((uint32_t)vs.sizes[i] - p.hdr_bits + 1u) & 3u);
             __syncthreads();
             // ---- second pass with the chosen sizes (encoder_vbr.rs:193-207)
-            if (FB >= 0) search_pass_fast<FB>(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
-            else search_pass(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_buf, sf_sec_bit, res_sec_bit, vs);
+            if (FB >= 0) search_pass_fast<FB>(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            else search_pass(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
         }
         __syncthreads();
 
