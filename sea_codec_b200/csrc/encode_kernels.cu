@@ -355,16 +355,29 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             // arg-min over the 16 candidates of the chain: strict total order (rank, ord); ord follows from the lane.  (Three
             // REDUX min-reductions -- high word, low word, order -- need a third of the instructions but measured 5 % slower at
             // 1024 streams: their latency sits on the per-block critical path of a latency-bound kernel.)
-            unsigned long long g_rank = rank;
-            uint32_t g_lane = lane;
+            uint32_t g_lane;
+            if (!__any_sync(0xffffffffu, (rank >> 60) != 0ull)) {
+                // the usual case: (rank, ord) fits one 64-bit key, a butterfly of 64-bit minima finds the winner's order and
+                // the lane follows from it: sf = (ord + prev) mod 16 (encoder_base.rs:116-117)
+                unsigned long long key = (rank << 4) | ord;
 #pragma unroll
-            for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
-                const unsigned long long o_rank = __shfl_xor_sync(0xffffffffu, g_rank, o);
-                const uint32_t o_lane = __shfl_xor_sync(0xffffffffu, g_lane, o);
-                const uint32_t g_ord = ((g_lane & 15u) - prev) & (nsf - 1u), o_ord = ((o_lane & 15u) - prev) & (nsf - 1u);
-                if (o_rank < g_rank || (o_rank == g_rank && o_ord < g_ord)) {
-                    g_rank = o_rank;
-                    g_lane = o_lane;
+                for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+                g_lane = grp * 16u + (((uint32_t)key + prev) & (nsf - 1u));
+            } else {  // ranks of 2^60 and more (runaway weights penalty): compare (rank, ord) explicitly
+                unsigned long long g_rank = rank;
+                g_lane = lane;
+#pragma unroll
+                for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
+                    const unsigned long long o_rank = __shfl_xor_sync(0xffffffffu, g_rank, o);
+                    const uint32_t o_lane = __shfl_xor_sync(0xffffffffu, g_lane, o);
+                    const uint32_t g_ord = ((g_lane & 15u) - prev) & (nsf - 1u), o_ord = ((o_lane & 15u) - prev) & (nsf - 1u);
+                    if (o_rank < g_rank || (o_rank == g_rank && o_ord < g_ord)) {
+                        g_rank = o_rank;
+                        g_lane = o_lane;
+                    }
                 }
             }
             // encoder_base.rs:181-186: the winner's state becomes the chain's state -- broadcast in registers
