@@ -274,6 +274,28 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             chh[i] = st_h[c * 4 + i];
         }
         uint32_t prev = (uint32_t)st_prev[c];
+        // ---- direct quantiser (CBR sizes 1..3): the lane's scale factor never changes, so the quantiser + dequantiser of
+        // encoder_base.rs:66-75 collapses to comparisons of A = 2|r| - (r < 0) against <= 3 per-lane thresholds and a select
+        // among <= 4 per-lane magnitudes -- no 64-bit multiply, no dependent table load on the step's critical path.
+        // k >= j  <=>  |n| >= m_j (m_j = 2j; size 2: 3) with n = (r*recip + 2^15) >> 16:
+        //   r >= 0: r >= ceil(X/recip),  r < 0: |r| >= floor(X/recip) + 1,  X = 65536*m_j - 32768;
+        // both in one unsigned compare A >= 2*ceil(X/recip) - 1 + [recip divides X] (A is even for r >= 0, odd for r < 0).
+        constexpr bool kDirect = FB >= 1 && FB <= 3;
+        constexpr int kLevels = FB == 3 ? 3 : (FB == 2 ? 1 : 0);
+        uint32_t theta[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+        int32_t mag[4] = {0, 0, 0, 0};
+        if (kDirect) {
+            const uint32_t rc = (uint32_t)fl.recip[sf];
+            const int32_t *row0 = tab + tab_dqt_off(4, FB > 0 ? FB : 1) + (sf << (FB > 0 ? FB : 1));
+#pragma unroll
+            for (int j = 0; j <= kLevels; j++) mag[j] = __ldg(row0 + 2 * j);  // dqt[sf][2k] = +round(sf * curve[k]) (dqt.rs:114-123)
+#pragma unroll
+            for (int j = 1; j <= kLevels; j++) {
+                const uint32_t m = FB == 2 ? 3u : 2u * (uint32_t)j;
+                const uint32_t X = 65536u * m - 32768u, q = X / rc, rem = X - q * rc;
+                theta[j - 1] = rem ? 2u * (q + 1u) - 1u : 2u * q;  // 2*ceil - 1 + [divides]
+            }
+        }
         for (uint32_t blk = 0; blk < nblk; blk++) {
             uint32_t nf = frames - blk * F;
             if (nf > F) nf = F;
@@ -317,13 +339,37 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                                          ((uint32_t)w[2] * (uint32_t)h[2] + (uint32_t)w[3] * (uint32_t)h[3]);
                     const int32_t pr = (int32_t)acc >> 13;
                     const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
+                    uint32_t code;
+                    int32_t d;
+                    if (kDirect) {
+                        const int32_t ms = r >> 31;                                      // 0 / -1
+                        const uint32_t A = ((uint32_t)r << 1) ^ (uint32_t)ms;            // 2|r| - (r < 0)
+                        int32_t mg = mag[0];
+                        uint32_t k2 = 0;
+                        if (kLevels == 3) {  // two select levels instead of a chain of three
+                            const bool p1 = A >= theta[0], p2 = A >= theta[1], p3 = A >= theta[2];
+                            const int32_t lo = p1 ? mag[1] : mag[0], hi = p3 ? mag[3] : mag[2];
+                            mg = p2 ? hi : lo;
+                            k2 = p2 ? (p3 ? 6u : 4u) : (p1 ? 2u : 0u);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < kLevels; j++) {
+                                const bool ge = A >= theta[j];
+                                mg = ge ? mag[j + 1] : mg;
+                                k2 = ge ? 2u * (uint32_t)(j + 1) : k2;
+                            }
+                        }
+                        d = (mg ^ ms) - ms;                                              // odd code = negative (dqt.rs:118-121)
+                        code = k2 - (uint32_t)ms;                                        // 2k + (r < 0)
+                    } else {
                     const int32_t n = (int32_t)(((int64_t)r * (int64_t)recip + 32768) >> 16);
                     const uint32_t an = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;
                     // qt.rs:9-31 closed form: 2*min(an >> 1, kmax) == min(an, 2*kmax + 1) & ~1 (size 2: magnitude index is an >= 3)
                     uint32_t k2 = (an < 2u * kmax + 1u ? an : 2u * kmax + 1u) & ~1u;
                     if ((FB > 0 ? (uint32_t)FB : size) == 2u) k2 = an >= 3u ? 2u : 0u;
-                    const uint32_t code = k2 + ((uint32_t)r >> 31);
-                    const int32_t d = kMode == kEncLutGlobal ? __ldg(row + code) : row[code << (kMode == kEncLut32 ? 5 : 4)];
+                    code = k2 + ((uint32_t)r >> 31);
+                    d = kMode == kEncLutGlobal ? __ldg(row + code) : row[code << (kMode == kEncLut32 ? 5 : 4)];
+                    }
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
                     const int32_t y = clamp_i16(v);
                     rank = rank_step<kNarrow>(rank, xv - y, w);
