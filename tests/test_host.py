@@ -183,3 +183,33 @@ def test_c_headers_compile_as_c_and_cpp(tmp_path):
     cpp = tmp_path / "t.cpp"
     cpp.write_text('#include "sea_b200.hpp"\nint main() { sea::EncoderSettings s; return s.frames_per_chunk == 5120 ? 0 : 1; }\n')
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, str(cpp)], check=True)
+
+
+def test_direct_quantiser_thresholds_equal_the_closed_form():
+    """encode_kernels.cu (kDirect, CBR sizes 1..3) replaces n = (r*recip + 2^15) >> 16, k = min(|n| >> 1, kmax) (size 2:
+    |n| >= 3) by comparisons of A = 2|r| - (r < 0) against theta_j = 2*ceil(X/recip) - 1 + [recip divides X],
+    X = 65536*m_j - 32768.  Exhaustive over every reciprocal of the sf-bits-4 tables, plus reciprocals that divide X exactly
+    (the case where the positive and the negative threshold differ), and every residual in +-70000."""
+    L = S.lib()
+    recips = set()
+    for b in (1, 2, 3):
+        rc = np.zeros(16, dtype=np.int32)
+        dq = np.zeros(16 << b, dtype=np.int32)
+        assert L.sea_b200_tables(b, 4, rc.ctypes.data, dq.ctypes.data) == 0
+        recips.update(int(x) for x in rc)
+    recips.update([32768, 16384, 4096, 98304 // 3, 229376 // 7, 65536, 10922, 3, 1])  # several divide some X exactly
+    r = np.arange(-70000, 70001, dtype=np.int64)
+    A = (2 * np.abs(r) - (r < 0)).astype(np.int64)
+    for b, ms in ((3, (2, 4, 6)), (2, (3,))):
+        kmax = (1 << (b - 1)) - 1
+        for rc in sorted(recips):
+            n = (r * rc + 32768) >> 16
+            an = np.abs(n)
+            want = np.minimum(an >> 1, kmax) if b != 2 else (an >= 3).astype(np.int64)
+            got = np.zeros_like(r)
+            for m in ms:
+                X = 65536 * m - 32768
+                q, rem = divmod(X, rc)
+                theta = 2 * (q + 1) - 1 if rem else 2 * q
+                got += (A >= theta)
+            assert np.array_equal(got, want), (b, rc)
