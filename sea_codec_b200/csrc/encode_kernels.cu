@@ -367,8 +367,16 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     // qt.rs:9-31 closed form: 2*min(an >> 1, kmax) == min(an, 2*kmax + 1) & ~1 (size 2: magnitude index is an >= 3)
                     uint32_t k2 = (an < 2u * kmax + 1u ? an : 2u * kmax + 1u) & ~1u;
                     if ((FB > 0 ? (uint32_t)FB : size) == 2u) k2 = an >= 3u ? 2u : 0u;
-                    code = k2 + ((uint32_t)r >> 31);
-                    d = kMode == kEncLutGlobal ? __ldg(row + code) : row[code << (kMode == kEncLut32 ? 5 : 4)];
+                    // the sign bit is known long before k2: fold it into the row pointer so that the table address is one
+                    // multiply-add after k2 (code itself is only needed for the bit stream)
+                    const uint32_t sbit = (uint32_t)r >> 31;
+                    code = k2 + sbit;
+                    if (kMode == kEncLutGlobal) {
+                        d = __ldg(row + sbit + k2);
+                    } else {
+                        const int32_t *rs = row + (sbit << (kMode == kEncLut32 ? 5 : 4));
+                        d = rs[k2 << (kMode == kEncLut32 ? 5 : 4)];
+                    }
                     }
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
                     const int32_t y = clamp_i16(v);
