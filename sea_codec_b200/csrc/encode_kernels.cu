@@ -42,6 +42,8 @@ struct VbrScratch {
     uint32_t *blkbit;          // bit offset of each block         [nblk]
     uint32_t *rowbits;         // bits per frame of each block     [nblk]
     uint8_t *sizes;            // residual size per (block, channel)
+    uint32_t *desc;            // per (block, channel): size | prefix bits << 4 | frame bits << 12 (second pass)  [items]
+    uint32_t desc_sh, blkbit_sh;  // shared-window addresses of desc / blkbit when the scratch lives in shared memory, else 0
 };
 
 static __host__ __device__ inline uint32_t next_pow2(uint32_t v)
@@ -55,7 +57,7 @@ uint64_t enc_vbr_scratch_bytes(const EncParams &p)
 {
     if (!p.vbr) return 0;
     const uint64_t nblk = p.N / p.F, items = nblk * p.channels, np2 = next_pow2((uint32_t)items);
-    uint64_t bytes = np2 * 8 + np2 * 4 + nblk * 4 + nblk * 4 + items;
+    uint64_t bytes = np2 * 8 + np2 * 4 + nblk * 4 + nblk * 4 + items * 4 + items;
     return (bytes + 255) & ~(uint64_t)255;
 }
 
@@ -67,7 +69,9 @@ __device__ __forceinline__ VbrScratch carve_scratch(uint8_t *base, const EncPara
     v.idx = reinterpret_cast<uint32_t *>(base + (uint64_t)np2 * 8);
     v.blkbit = v.idx + np2;
     v.rowbits = v.blkbit + nblk;
-    v.sizes = reinterpret_cast<uint8_t *>(v.rowbits + nblk);
+    v.desc = v.rowbits + nblk;
+    v.sizes = reinterpret_cast<uint8_t *>(v.desc + items);
+    v.desc_sh = v.blkbit_sh = 0;
     return v;
 }
 
@@ -308,7 +312,12 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 nx0 = __ldg(px + cb);
                 nx1 = __ldg(px + (cb + 1u < C ? cb + 1u : C - 1u));
             }
-            const uint32_t size = FB > 0 ? (uint32_t)FB : (mode == 2 ? (uint32_t)vs.sizes[blk * C + c] : uniform_size);
+            uint32_t bdesc = 0;  // second VBR pass: size | prefix << 4 | frame bits << 12 of this (block, channel)
+            if (FB == 0 && mode == 2) {
+                if (vs.desc_sh) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bdesc) : "r"(vs.desc_sh + (blk * C + c) * 4u));
+                else bdesc = vs.desc[blk * C + c];
+            }
+            const uint32_t size = FB > 0 ? (uint32_t)FB : (mode == 2 ? (bdesc & 15u) : uniform_size);
             const uint32_t slot = FB > 0 ? 0u : size - fl.lo_size;
             const int32_t recip = fl.recip[slot * 16u + sf];
             // shared [code][lane] / [code][sf] (two chains share a row) / global [sf][code]: see kEncLut*
@@ -448,10 +457,10 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             if (mode != 1 && active) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
                 uint32_t blockbit, rowbits, prefix;
                 if (mode == 2) {
-                    blockbit = vs.blkbit[blk];
-                    rowbits = vs.rowbits[blk];
-                    prefix = 0;
-                    for (uint32_t cc = 0; cc < c; cc++) prefix += vs.sizes[blk * C + cc];
+                    if (vs.blkbit_sh) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(blockbit) : "r"(vs.blkbit_sh + blk * 4u));
+                    else blockbit = vs.blkbit[blk];
+                    rowbits = bdesc >> 12;
+                    prefix = (bdesc >> 4) & 255u;
                 } else {
                     rowbits = C * size;
                     blockbit = blk * F * rowbits;
@@ -560,7 +569,13 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
     }
 
     VbrScratch vs = {};
-    if (p.vbr) vs = carve_scratch(p.vbr_smem_off ? smem + p.vbr_smem_off : ws.vbr_scratch + (uint64_t)sidx * ws.vbr_scratch_stride, p);
+    if (p.vbr) {
+        vs = carve_scratch(p.vbr_smem_off ? smem + p.vbr_smem_off : ws.vbr_scratch + (uint64_t)sidx * ws.vbr_scratch_stride, p);
+        if (p.vbr_smem_off) {  // typed shared-memory access for the per-block reads of the second pass
+            vs.desc_sh = (uint32_t)__cvta_generic_to_shared(vs.desc);
+            vs.blkbit_sh = (uint32_t)__cvta_generic_to_shared(vs.blkbit);
+        }
+    }
 
     // EncoderBase::new (encoder_base.rs:29-41, lms.rs:19-32) or the state kept by a streaming handle
     for (uint32_t c = tid; c < C; c += T) {
@@ -676,8 +691,17 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
                 }
                 sh_res_bits = acc;
             }
-            for (uint32_t i = tid; i < items; i += T)  // chunk.rs:245-252 (release build masks to 2 bits)
-                put_bits(chunk_sh, vbr_sec_bit + 2u * i, 2u, ((uint32_t)vs.sizes[i] - p.hdr_bits + 1u) & 3u);
+            for (uint32_t i = tid; i < items; i += T) {  // chunk.rs:245-252 (release build masks to 2 bits)
+                const uint32_t sz = vs.sizes[i], blk_i = i / C, c_i = i - blk_i * C;
+                put_bits(chunk_sh, vbr_sec_bit + 2u * i, 2u, (sz - p.hdr_bits + 1u) & 3u);
+                uint32_t prefix = 0, rb = 0;
+                for (uint32_t cc = 0; cc < C; cc++) {
+                    const uint32_t z = vs.sizes[blk_i * C + cc];
+                    prefix += cc < c_i ? z : 0u;
+                    rb += z;
+                }
+                vs.desc[i] = sz | (prefix << 4) | (rb << 12);
+            }
             __syncthreads();
             // ---- second pass with the chosen sizes (encoder_vbr.rs:193-207)
             if (FB >= 0) search_pass_fast<FB>(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
