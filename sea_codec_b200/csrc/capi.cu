@@ -214,8 +214,10 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
     std::vector<DecStream> table(job.streams);
     const bool use_vbr = fast && decode_vbr_supported(fp);  // the VBR twin of the unrolled kernel: same split, same constraints
-    bool unrolled = fast && (use_vbr || decode_unrolled_supported(fp)) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
-    const uint64_t tail_slack = use_vbr ? 320u : 128u;     // bytes both kernels may read past the last chunk they are given
+    // more than two channels (CBR): lanes per (chunk, channel pair), decode_mc.cu; its left-overs go to the generic kernel
+    bool mc = !fast && fp.channels > 2 && (fp.hdr_word >> 24) == 0x5Au && decode_mc_supported(fp);
+    bool unrolled = ((fast && (use_vbr || decode_unrolled_supported(fp))) || mc) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
+    const uint64_t tail_slack = mc ? 512u : (use_vbr ? 320u : 128u);  // bytes the kernels may read past the last chunk they are given
     uint64_t chains_a = 0, chains_b = 0;
     if (unrolled) {
         table.resize((size_t)3 * n_streams);
@@ -241,6 +243,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
         }
         if (chains_a == 0) unrolled = false;
     }
+    if (!unrolled) mc = false;  // no staged kernel for more than two channels: everything goes to the generic one
     CU(L.table->reserve(sizeof(DecStream) * table.size()));
     CU(cudaMemcpyAsync(L.table->p, table.data(), sizeof(DecStream) * table.size(), cudaMemcpyHostToDevice, L.stream));
     CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
@@ -248,7 +251,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
 
     CU(cudaEventRecord(L.ev0, L.stream));
     int dev_err = 0;
-    if (fast) {
+    if (fast || mc) {
         if (unrolled) {
             DecFastParams fa = fp, fb = fp;
             fa.total_chunks = chains_a / fp.channels;
@@ -258,11 +261,13 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
             if (fb.total_chunks) {
                 CU(cudaEventRecord(L.ev_fork, L.stream));
                 CU(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
-                CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, L.d_err, L.side));
+                if (mc) CU(launch_decode_generic(d_sea, d_pcm, d_all + 2 * (size_t)n_streams, n_streams, chains_b, ctx->tabs, L.d_err, L.side));
+                else CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, L.d_err, L.side));
                 ctx->launches++;
                 CU(cudaEventRecord(L.ev_join, L.side));
             }
-            if (use_vbr) CU(launch_decode_vbr(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
+            if (mc) CU(launch_decode_mc(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
+            else if (use_vbr) CU(launch_decode_vbr(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
             else CU(launch_decode_unrolled(d_sea, d_pcm, d_all + n_streams, fa, ctx->tabs, L.d_err, L.stream));
             ctx->launches++;
             if (fb.total_chunks) CU(cudaStreamWaitEvent(L.stream, L.ev_join, 0));
@@ -274,10 +279,11 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
         CU(cudaStreamSynchronize(L.stream));
         if (dev_err != kDevOk) {  // some chunk is not what the fast path was specialised for: redo everything generically
             fast = false;
+            mc = false;
             CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
         }
     }
-    if (!fast) {
+    if (!fast && !mc) {
         CU(launch_decode_generic(d_sea, d_pcm, d_all, n_streams, job.total_chains, ctx->tabs, L.d_err, L.stream));
         ctx->launches++;
         CU(cudaMemcpyAsync(&dev_err, L.d_err, sizeof(int), cudaMemcpyDeviceToHost, L.stream));

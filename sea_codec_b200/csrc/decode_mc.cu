@@ -1,0 +1,255 @@
+// decode_mc.cu -- throughput decode for uniform CBR batches with MORE than two channels (4, 6 or 8; BASELINE config 3 is an
+// 8-channel stream): decode_mc_kernel<CT, B>.
+//
+// Lane mapping: one lane per (chunk, channel PAIR).  In the [frame][channel] bit stream (chunk.rs:254-278) the two codes of a
+// pair are adjacent, and the pairs of one frame follow each other, so lane (g, p) reads a stereo-like stream whose frames are
+// CT*B bits apart, starting 2*p*B bits into the residual section.  Each lane keeps two LMS chains in registers (the ILP of the
+// stereo kernel) and CT/2 neighbouring lanes cover one chunk.  Everything else is borrowed from decode_unrolled_kernel /
+// decode_vbr_kernel: per-lane cp.async ring (every lane stages the chunk's bytes it walks through), a window of big-endian
+// words per body pre-shifted once so that every field position inside the body is a compile-time constant, one shift per pair of
+// codes, I2IP pack-saturate clamp, LMS signs carried in registers.  PCM: one 32-bit store per frame and lane; the CT/2 lanes of a
+// chunk write the CT interleaved samples of a frame side by side.
+#include "sea_kernels.h"
+
+namespace sea {
+
+namespace {
+
+__device__ __forceinline__ void report_m(int *err, int code) { atomicCAS(err, 0, code); }
+__device__ __forceinline__ uint32_t smem_u32m(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_ifm(bool pred, uint32_t dst, const void *src)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}" ::"r"((int)pred), "r"(dst), "l"(src)
+        : "memory");
+}
+__device__ __forceinline__ void cp_commit_m() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait1_m() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait0_m() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u32m(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds_s32m(uint32_t addr)
+{
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t find_stream_m(const DecStream *streams, uint32_t n_streams, uint64_t chain)
+{
+    uint32_t lo = 0, hi = n_streams;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)streams[mid].chain_begin <= chain) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int CT, int B>
+struct MCfg {
+    static constexpr int F = 20;
+    static constexpr int U = CT / 2;                    // lanes per chunk
+    static constexpr int kChunksPerWarp = 32 / U;       // CT = 6: 10 chunks, two idle lanes
+    static constexpr int HF = CT >= 6 ? 10 : 20;        // frames per looped body (divides F)
+    static constexpr int kBodyBits = HF * CT * B;       // bits of the stream one body walks through
+    static constexpr int kNW = (kBodyBits - (CT - 2) * B + 31 + 31) / 32;  // window words from my first field to my last (any phase)
+    static constexpr int kBodyBytesMax = (kBodyBits + 7) / 8 + 1;
+    static constexpr int kRingWords = 64;               // 256-byte ring per lane: two bodies (<= 80 bytes each) plus slack
+    static constexpr int kTopUp = (kBodyBytesMax + 15) / 16 + 1;  // granules issued per body at most
+    static constexpr int kPitch = 256 + 16;
+    static constexpr int kWarpBytes = 32 * kPitch + 64;
+    static constexpr int kWarps = 12;
+    static_assert(2 * kBodyBytesMax + 32 <= 256, "ring too small for two bodies");
+};
+
+}  // namespace
+
+template <int CT, int B>
+__global__ void __launch_bounds__(MCfg<CT, B>::kWarps * 32, 1)
+decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams, DecFastParams p,
+                 const int32_t *__restrict__ tab, int *err)
+{
+    using Cfg = MCfg<CT, B>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t s = 4;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    // dequant rows of size B as uploaded: lut[sf][code]
+    int32_t *lut = reinterpret_cast<int32_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
+    for (uint32_t i = threadIdx.x; i < (1u << (s + B)); i += blockDim.x) lut[i] = tab[tab_dqt_off(s, B) + i];
+    __syncthreads();
+    const uint32_t lut_sh = smem_u32m(lut);
+
+    const uint32_t pr = lane % Cfg::U;                              // my channel pair
+    uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kChunksPerWarp + lane / Cfg::U;  // global chunk index
+    const bool valid = lane < (uint32_t)(Cfg::kChunksPerWarp * Cfg::U) && g < p.total_chunks;
+    if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
+
+    const DecStream st = streams[find_stream_m(streams, p.n_streams, g * CT)];
+    const uint32_t k = (uint32_t)(g - st.chain_begin / CT);
+    const uint64_t ck_off = st.data_off + (uint64_t)k * p.chunk_size;
+    const uint8_t *ck = sea + ck_off;
+    {
+        const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
+        if (word != p.hdr_word) report_m(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
+    }
+    int32_t w[2][4], h[2][4], sg[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const uint8_t *l = ck + 4u + 16u * (2u * pr + c);  // lms.rs:80-94
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            h[c][i] = (int16_t)(l[2 * i] | (l[2 * i + 1] << 8));
+            w[c][i] = (int16_t)(l[8 + 2 * i] | (l[8 + 2 * i + 1] << 8));
+            sg[c][i] = (h[c][i] >> 31) | 1;
+        }
+    }
+    const uint32_t items = (p.N / Cfg::F) * CT;
+    const uint64_t sf_off = ck_off + 4u + 16u * CT;              // chunk.rs:108-113
+    const uint64_t res_off = sf_off + items / 2u;                // s == 4: two scale factors per byte, items even
+    const uint8_t *sfp = sea + sf_off + pr;                      // my pair's byte of block b: sfp[b * U]
+    uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * CT) + 4u * pr;
+
+    // ---- per-lane ring.  Word w of the 16-byte aligned stream sits at ring word (w & 63).
+    const uint64_t a0 = res_off & ~(uint64_t)15;
+    const uint8_t *src0 = sea + a0;
+    const uint32_t ring_sh = smem_u32m(smem + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
+    uint32_t fetched = 0;                                        // granules issued so far
+    uint32_t posg = (uint32_t)(res_off - a0) * 8u;               // bit position of the current body's first field, from a0
+#pragma unroll
+    for (int t = 0; t < 16; t++) cp_async16_ifm(true, ring_sh + t * 16, src0 + t * 16);
+    fetched = 16;
+    cp_commit_m();
+    cp_commit_m();
+    cp_wait0_m();
+
+    const uint32_t n_bodies = p.N / Cfg::HF;
+    constexpr int kBodiesPerBlock = Cfg::F / Cfg::HF;
+    uint32_t sfb = __ldg(sfp);  // scale-factor byte of block 0: high nibble = first channel of the pair
+
+    for (uint32_t bd = 0; bd < n_bodies; bd++) {
+        // ---- top the ring up, then wait for everything but that (the bytes of this body were issued a body ago)
+        {
+            const uint32_t wq = posg >> 5;
+#pragma unroll
+            for (int t = 0; t < Cfg::kTopUp; t++) {
+                const bool room = fetched * 4u + 4u <= wq + (uint32_t)Cfg::kRingWords;
+                cp_async16_ifm(room, ring_sh + (fetched & 15u) * 16u, src0 + (size_t)fetched * 16u);
+                fetched += room ? 1u : 0u;
+            }
+            cp_commit_m();
+            cp_wait1_m();
+        }
+        // scale factors of this body's block (one byte per block and pair); the next block's byte is fetched a body ahead
+        const uint32_t blk = bd / kBodiesPerBlock;
+        const uint32_t sf_cur = sfb;
+        if ((bd % kBodiesPerBlock) == kBodiesPerBlock - 1 && bd + 1 < n_bodies) sfb = __ldg(sfp + (size_t)(blk + 1u) * Cfg::U);
+        uint32_t rowbase[2];
+        rowbase[0] = lut_sh + (((sf_cur >> 4) & 15u) << (B + 2));
+        rowbase[1] = lut_sh + ((sf_cur & 15u) << (B + 2));
+
+        // ---- window: big-endian words from my first field of this body on, pre-shifted so that it starts at bit 0 of W[0]
+        const uint32_t my = posg + 2u * B * pr;
+        const uint32_t w0 = my >> 5, sh = my & 31u;
+        uint32_t V[Cfg::kNW + 1], W[Cfg::kNW];
+#pragma unroll
+        for (int t = 0; t < Cfg::kNW + 1; t++) V[t] = __byte_perm(lds_u32m(ring_sh + ((w0 + t) & 63u) * 4u), 0, 0x0123);
+#pragma unroll
+        for (int t = 0; t < Cfg::kNW; t++) W[t] = __funnelshift_l(V[t + 1], V[t], sh);
+        posg += Cfg::kBodyBits;
+
+        uint8_t *ob = out + (size_t)bd * (Cfg::HF * CT * 2);
+#pragma unroll
+        for (int fi = 0; fi < Cfg::HF; fi++) {
+            constexpr int kGB = 2 * B;
+            const int bit = fi * CT * B;  // compile-time position of my pair of codes in W[]
+            const int wd = bit >> 5, off = bit & 31;
+            uint32_t x;  // the two codes in the low 2B bits
+            if (off + kGB <= 32) x = W[wd] >> (32 - off - kGB);
+            else x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - kGB) & 31);
+            int32_t y[2], d[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint32_t code = c == 0 ? (x >> B) & ((1u << B) - 1u) : x & ((1u << B) - 1u);
+                d[c] = lds_s32m(rowbase[c] + code * 4u);
+                const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
+                                     (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
+                y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:38, before the clamp
+            }
+            int32_t sgn[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) sgn[c] = (y[c] >> 31) | 1;  // the clamp keeps the sign
+            uint32_t packed;
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[1]), "r"(y[0]));  // clamp_i16 x2 + interleave
+            y[0] = (int32_t)(int16_t)(packed & 0xffffu);
+            y[1] = (int32_t)packed >> 16;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int32_t delta = d[c] >> 4;  // lms.rs:43-51
+                w[c][0] += delta * sg[c][0];
+                w[c][1] += delta * sg[c][1];
+                w[c][2] += delta * sg[c][2];
+                w[c][3] += delta * sg[c][3];
+                h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
+                sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
+            }
+            if (valid) *reinterpret_cast<uint32_t *>(ob + fi * (CT * 2)) = packed;
+        }
+    }
+}
+
+bool decode_mc_supported(const DecFastParams &p)
+{
+    if (p.channels != 4 && p.channels != 6 && p.channels != 8) return false;
+    if ((p.hdr_word & 0xffu) != 1u) return false;  // CBR chunks only
+    if (p.F != 20 || p.s != 4 || p.b < 1 || p.b > 8) return false;
+    return p.N != 0 && p.N % 20u == 0;
+}
+
+template <int CT, int B>
+static cudaError_t launch_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, const int32_t *tab,
+                             int *d_err, cudaStream_t stream)
+{
+    using Cfg = MCfg<CT, B>;
+    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + ((size_t)4u << (4 + B));
+    cudaError_t e = cudaFuncSetAttribute(decode_mc_kernel<CT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kChunksPerWarp;
+    const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
+    decode_mc_kernel<CT, B><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    return cudaGetLastError();
+}
+
+template <int CT>
+static cudaError_t launch_mc_b(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, const int32_t *tab,
+                               int *d_err, cudaStream_t stream)
+{
+    switch (p.b) {
+        case 1: return launch_mc<CT, 1>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 2: return launch_mc<CT, 2>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 3: return launch_mc<CT, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 4: return launch_mc<CT, 4>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 5: return launch_mc<CT, 5>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 6: return launch_mc<CT, 6>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 7: return launch_mc<CT, 7>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        default: return launch_mc<CT, 8>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+    }
+}
+
+cudaError_t launch_decode_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
+                             int *d_err, cudaStream_t stream)
+{
+    if (p.total_chunks == 0) return cudaSuccess;
+    const int32_t *tab = tabs.by_s[p.s];
+    switch (p.channels) {
+        case 4: return launch_mc_b<4>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        case 6: return launch_mc_b<6>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+        default: return launch_mc_b<8>(d_sea, d_pcm, d_streams, p, tab, d_err, stream);
+    }
+}
+
+}  // namespace sea

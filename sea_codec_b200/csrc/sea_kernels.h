@@ -53,6 +53,12 @@ bool decode_vbr_supported(const DecFastParams &p);
 cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
                               int *d_err, cudaStream_t stream);
 
+// More than two channels (decode_mc.cu): CBR, 4 / 6 / 8 channels, scale_factor_bits = 4, scale_factor_frames = 20, FULL chunks only,
+// the same alignment rules, >= 512 readable bytes after every chunk it is given.
+bool decode_mc_supported(const DecFastParams &p);
+cudaError_t launch_decode_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
+                             int *d_err, cudaStream_t stream);
+
 // ---- encode ------------------------------------------------------------------------------------------------
 struct EncStream {
     uint64_t pcm_off;   // sample offset of the stream's PCM

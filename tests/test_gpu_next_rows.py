@@ -309,3 +309,25 @@ def test_corrupted_files_never_disagree_with_the_oracle(ctx, oracle):
         if ok_o:
             assert all(np.array_equal(g, want) for g in got_b), (case, kind, "batch")
     assert n_ok >= 10 and n_err >= 10, (n_ok, n_err)
+
+
+@pytest.mark.parametrize("channels", [4, 6, 8])
+@pytest.mark.parametrize("bits", [1, 3, 4, 5, 8])
+def test_multichannel_pair_lane_kernel(ctx, oracle, channels, bits):
+    """decode_mc_kernel (lane per chunk and channel pair): uniform CBR batches with 4 / 6 / 8 channels, several full chunks per
+    stream plus a ragged tail (taken by the generic kernel on the side stream), quiet / loud / ordinary signals."""
+    files, refs = [], []
+    for i in range(5):
+        frames = 5120 * (1 + i % 3) + (i * 997) % 5120
+        if i % 3 == 1:
+            t = np.arange(frames * channels)
+            pcm = np.clip(38000 * np.sin(t * 0.011 * (1 + t % channels)), -32768, 32767).astype(np.int16)
+        elif i % 3 == 2:
+            pcm = np.random.default_rng(50 + i).integers(-500, 501, frames * channels).astype(np.int16)
+        else:
+            pcm = synth.gen_stream(400 + i, frames, channels, 48000)
+        enc = oracle.sea_encode(pcm, 48000, channels, oracle.make_settings(float(bits)))
+        files.append(enc)
+        refs.append(oracle.sea_decode(enc).samples)
+    for o, r in zip(ctx.decode_batch(files), refs):
+        assert np.array_equal(o.samples, r)
