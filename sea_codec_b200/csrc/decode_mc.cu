@@ -52,11 +52,12 @@ __device__ __forceinline__ uint32_t find_stream_m(const DecStream *streams, uint
 template <int CT, int B>
 struct MCfg {
     static constexpr int F = 20;
-    static constexpr int U = CT / 2;                    // lanes per chunk
+    static constexpr int CPL = (CT % 4 == 0) ? 4 : 2;   // channels per lane: a quad where the count allows (fewer memory instructions per sample)
+    static constexpr int U = CT / CPL;                  // lanes per chunk
     static constexpr int kChunksPerWarp = 32 / U;       // CT = 6: 10 chunks, two idle lanes
     static constexpr int HF = CT >= 6 ? 10 : 20;        // frames per looped body (divides F)
     static constexpr int kBodyBits = HF * CT * B;       // bits of the stream one body walks through
-    static constexpr int kNW = (kBodyBits - (CT - 2) * B + 31 + 31) / 32;  // window words from my first field to my last (any phase)
+    static constexpr int kNW = (kBodyBits - (CT - CPL) * B + 31 + 31) / 32;  // window words from my first field to my last (any phase)
     static constexpr int kBodyBytesMax = (kBodyBits + 7) / 8 + 1;
     static constexpr int kRingWords = 64;               // 256-byte ring per lane: two bodies (<= 80 bytes each) plus slack
     static constexpr int kTopUp = (kBodyBytesMax + 15) / 16 + 1;  // granules issued per body at most
@@ -84,7 +85,8 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     __syncthreads();
     const uint32_t lut_sh = smem_u32m(lut);
 
-    const uint32_t pr = lane % Cfg::U;                              // my channel pair
+    constexpr int CPL = Cfg::CPL;
+    const uint32_t pr = lane % Cfg::U;                              // my channel group (pair or quad)
     uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kChunksPerWarp + lane / Cfg::U;  // global chunk index
     const bool valid = lane < (uint32_t)(Cfg::kChunksPerWarp * Cfg::U) && g < p.total_chunks;
     if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
@@ -97,10 +99,10 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
         const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
         if (word != p.hdr_word) report_m(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
     }
-    int32_t w[2][4], h[2][4], sg[2][4];
+    int32_t w[CPL][4], h[CPL][4], sg[CPL][4];
 #pragma unroll
-    for (int c = 0; c < 2; c++) {
-        const uint8_t *l = ck + 4u + 16u * (2u * pr + c);  // lms.rs:80-94
+    for (int c = 0; c < CPL; c++) {
+        const uint8_t *l = ck + 4u + 16u * (CPL * pr + c);  // lms.rs:80-94
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             h[c][i] = (int16_t)(l[2 * i] | (l[2 * i + 1] << 8));
@@ -111,8 +113,8 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     const uint32_t items = (p.N / Cfg::F) * CT;
     const uint64_t sf_off = ck_off + 4u + 16u * CT;              // chunk.rs:108-113
     const uint64_t res_off = sf_off + items / 2u;                // s == 4: two scale factors per byte, items even
-    const uint8_t *sfp = sea + sf_off + pr;                      // my pair's byte of block b: sfp[b * U]
-    uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * CT) + 4u * pr;
+    const uint8_t *sfp = sea + sf_off + pr * (CPL / 2);          // my group's CPL/2 bytes of block b: sfp[b * CT/2 ...]
+    uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * CT) + 2u * CPL * pr;
 
     // ---- per-lane ring.  Word w of the 16-byte aligned stream sits at ring word (w & 63).
     const uint64_t a0 = res_off & ~(uint64_t)15;
@@ -129,7 +131,12 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
 
     const uint32_t n_bodies = p.N / Cfg::HF;
     constexpr int kBodiesPerBlock = Cfg::F / Cfg::HF;
-    uint32_t sfb = __ldg(sfp);  // scale-factor byte of block 0: high nibble = first channel of the pair
+    // scale-factor nibbles of a block for my channels, first channel in the top nibble of the CPL*4-bit value
+    auto load_sf = [&](uint32_t blk) -> uint32_t {
+        const uint8_t *q = sfp + (size_t)blk * (CT / 2);
+        return CPL == 4 ? ((uint32_t)__ldg(q) << 8) | (uint32_t)__ldg(q + 1) : (uint32_t)__ldg(q);
+    };
+    uint32_t sfb = load_sf(0);
 
     for (uint32_t bd = 0; bd < n_bodies; bd++) {
         // ---- top the ring up, then wait for everything but that (the bytes of this body were issued a body ago)
@@ -147,13 +154,13 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
         // scale factors of this body's block (one byte per block and pair); the next block's byte is fetched a body ahead
         const uint32_t blk = bd / kBodiesPerBlock;
         const uint32_t sf_cur = sfb;
-        if ((bd % kBodiesPerBlock) == kBodiesPerBlock - 1 && bd + 1 < n_bodies) sfb = __ldg(sfp + (size_t)(blk + 1u) * Cfg::U);
-        uint32_t rowbase[2];
-        rowbase[0] = lut_sh + (((sf_cur >> 4) & 15u) << (B + 2));
-        rowbase[1] = lut_sh + ((sf_cur & 15u) << (B + 2));
+        if ((bd % kBodiesPerBlock) == kBodiesPerBlock - 1 && bd + 1 < n_bodies) sfb = load_sf(blk + 1u);
+        uint32_t rowbase[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; c++) rowbase[c] = lut_sh + (((sf_cur >> (4 * (CPL - 1 - c))) & 15u) << (B + 2));
 
         // ---- window: big-endian words from my first field of this body on, pre-shifted so that it starts at bit 0 of W[0]
-        const uint32_t my = posg + 2u * B * pr;
+        const uint32_t my = posg + (uint32_t)(CPL * B) * pr;
         const uint32_t w0 = my >> 5, sh = my & 31u;
         uint32_t V[Cfg::kNW + 1], W[Cfg::kNW];
 #pragma unroll
@@ -163,32 +170,34 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
         posg += Cfg::kBodyBits;
 
         uint8_t *ob = out + (size_t)bd * (Cfg::HF * CT * 2);
+        uint32_t ow[8];  // U == 1: four frames being assembled into one 32-byte store
 #pragma unroll
         for (int fi = 0; fi < Cfg::HF; fi++) {
-            constexpr int kGB = 2 * B;
-            const int bit = fi * CT * B;  // compile-time position of my pair of codes in W[]
+            constexpr int kGB = CPL * B;
+            const int bit = fi * CT * B;  // compile-time position of my group of codes in W[]
             const int wd = bit >> 5, off = bit & 31;
-            uint32_t x;  // the two codes in the low 2B bits
+            uint32_t x;  // my CPL codes in the low CPL*B bits, first channel highest
             if (off + kGB <= 32) x = W[wd] >> (32 - off - kGB);
             else x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - kGB) & 31);
-            int32_t y[2], d[2];
+            int32_t y[CPL], d[CPL], sgn[CPL];
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const uint32_t code = c == 0 ? (x >> B) & ((1u << B) - 1u) : x & ((1u << B) - 1u);
+            for (int c = 0; c < CPL; c++) {
+                const uint32_t code = (x >> (B * (CPL - 1 - c))) & ((1u << B) - 1u);
                 d[c] = lds_s32m(rowbase[c] + code * 4u);
                 const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                      (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                 y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:38, before the clamp
+                sgn[c] = (y[c] >> 31) | 1;                                            // the clamp keeps the sign
             }
-            int32_t sgn[2];
+            uint32_t packed[CPL / 2];
 #pragma unroll
-            for (int c = 0; c < 2; c++) sgn[c] = (y[c] >> 31) | 1;  // the clamp keeps the sign
-            uint32_t packed;
-            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[1]), "r"(y[0]));  // clamp_i16 x2 + interleave
-            y[0] = (int32_t)(int16_t)(packed & 0xffffu);
-            y[1] = (int32_t)packed >> 16;
+            for (int q = 0; q < CPL / 2; q++) {  // clamp_i16 x2 + interleave
+                asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed[q]) : "r"(y[2 * q + 1]), "r"(y[2 * q]));
+                y[2 * q] = (int32_t)(int16_t)(packed[q] & 0xffffu);
+                y[2 * q + 1] = (int32_t)packed[q] >> 16;
+            }
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
+            for (int c = 0; c < CPL; c++) {
                 const int32_t delta = d[c] >> 4;  // lms.rs:43-51
                 w[c][0] += delta * sg[c][0];
                 w[c][1] += delta * sg[c][1];
@@ -197,7 +206,20 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
                 h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
                 sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
             }
-            if (valid) *reinterpret_cast<uint32_t *>(ob + fi * (CT * 2)) = packed;
+            if (Cfg::U == 1) {
+                // the lane owns whole frames (CT == CPL == 4): four consecutive frames are one 32-byte sector -> 256-bit stores, as
+                // in the stereo kernel (8-byte stores to 32 different rows per instruction choked the L1 tag stage: 26 % issue)
+                ow[(fi & 3) * 2] = packed[0];
+                ow[(fi & 3) * 2 + 1] = packed[CPL / 2 - 1];
+                if ((fi & 3) == 3 && valid) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ob + (fi >> 2) * 32), "r"(ow[0]), "r"(ow[1]),
+                                 "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                                 : "memory");
+                }
+            } else if (valid) {
+                if (CPL == 4) *reinterpret_cast<uint2 *>(ob + fi * (CT * 2)) = make_uint2(packed[0], packed[CPL / 2 - 1]);
+                else *reinterpret_cast<uint32_t *>(ob + fi * (CT * 2)) = packed[0];
+            }
         }
     }
 }
