@@ -24,7 +24,8 @@ __device__ __forceinline__ void cp_async16_ifm(bool pred, uint32_t dst, const vo
         : "memory");
 }
 __device__ __forceinline__ void cp_commit_m() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait1_m() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait_keep() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_wait0_m() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lds_u32m(uint32_t addr)
 {
@@ -61,9 +62,14 @@ struct MCfg {
     static constexpr int kBodyBytesMax = (kBodyBits + 7) / 8 + 1;
     static constexpr int kRingWords = 64;               // 256-byte ring per lane: two bodies (<= 80 bytes each) plus slack
     static constexpr int kTopUp = (kBodyBytesMax + 15) / 16 + 1;  // granules issued per body at most
+    // The ring is kept full, so the bytes of a body were issued (256 - 32) / body bytes - 1 bodies before it is decoded: that many
+    // of the newest groups may still be in flight.  (Waiting for all but the newest one stalled every body on loads it would
+    // not need for another 4-5 bodies: long_scoreboard 1.35 per issue in profiles/r01_decode_mc_v2.)
+    static constexpr int kAhead = (256 - 32) / kBodyBytesMax - 1;
+    static constexpr int kKeep = kAhead < 1 ? 1 : (kAhead > 4 ? 4 : kAhead);
     static constexpr int kPitch = 256 + 16;
     static constexpr int kWarpBytes = 32 * kPitch + 64;
-    static constexpr int kWarps = 12;
+    static constexpr int kWarps = CT == 4 ? 16 : 12;    // measured: 4 channels 2.14 ms at 16 warps (2.46 at 12); 8 channels 7.36 ms at 12 (8.75 at 16)
     static_assert(2 * kBodyBytesMax + 32 <= 256, "ring too small for two bodies");
 };
 
@@ -149,7 +155,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
                 fetched += room ? 1u : 0u;
             }
             cp_commit_m();
-            cp_wait1_m();
+            cp_wait_keep<Cfg::kKeep>();
         }
         // scale factors of this body's block (one byte per block and pair); the next block's byte is fetched a body ahead
         const uint32_t blk = bd / kBodiesPerBlock;
