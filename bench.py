@@ -345,10 +345,10 @@ def main():
         del sea_v, sea_vu
         torch.cuda.empty_cache()
 
-    # ---- BASELINE config 3 shape (8 channels, 48 kHz, CBR 4; multichannel lane mapping): 64 streams of 60 s through decode_mc_kernel
+    # ---- BASELINE config 3 shape (8 channels, 48 kHz, CBR 4; multichannel lane mapping): 256 streams of 60 s through decode_mc_kernel
     mc_dec = None
     if not args.skip_encode:
-        ch8, rate8, fr8, n8, u8 = 8, 48000, 60 * 48000, 64, 4
+        ch8, rate8, fr8, n8, u8 = 8, 48000, 60 * 48000, 256, 4
         st8 = S.EncoderSettings(residual_bits=4.0)
         pcm8 = synth.gen_batch_torch(u8, fr8, ch8, rate8, dev, first_stream=first)
         b8 = ctx.encode_bound(fr8, ch8, st8)
