@@ -331,3 +331,19 @@ def test_multichannel_pair_lane_kernel(ctx, oracle, channels, bits):
         refs.append(oracle.sea_decode(enc).samples)
     for o, r in zip(ctx.decode_batch(files), refs):
         assert np.array_equal(o.samples, r)
+
+
+@pytest.mark.parametrize("channels,bits", [(1, 3), (2, 1), (2, 3), (2, 8), (4, 4), (6, 2), (8, 4), (3, 5)])
+def test_gpu_cbr_decode_against_the_reference_c_decoder(ctx, oracle, channels, bits):
+    """The strongest pin available without a Rust toolchain: the reference's OWN decoder (c/sea.h, compiled into oracle/_ref by
+    oracle/Makefile from the read-only reference tree) against the GPU decode kernels, on files the GPU encoder produced --
+    no restatement in between.  c/sea.h handles CBR with whole scale-factor blocks only (c/sea.h:131-134, :168)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    frames = 5120 * 3 + 2000  # a multiple of scale_factor_frames
+    pcm = synth.gen_stream(700 + channels * 10 + bits, frames, channels, 44100)
+    enc = ctx.sea_encode(pcm, 44100, channels, S.EncoderSettings(residual_bits=float(bits)))
+    want = oracle.ref_c_decode(enc).samples
+    assert np.array_equal(ctx.sea_decode(enc).samples, want)
+    for got in ctx.decode_batch([enc] * 5):  # the throughput kernels (unrolled / multichannel) + the tail kernels
+        assert np.array_equal(got.samples, want)

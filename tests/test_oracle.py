@@ -116,7 +116,8 @@ def test_vbr_outside_domain_panics(oracle):
         assert e.value.code == oracle.ERR_PANIC
 
 
-@pytest.mark.parametrize("channels,bits,sfb", [(1, 1, 4), (1, 3, 3), (2, 3, 4), (2, 8, 4), (3, 5, 5), (8, 4, 4), (2, 2, 4), (1, 6, 5)])
+@pytest.mark.parametrize("channels,bits,sfb", [(1, 1, 4), (1, 3, 3), (2, 3, 4), (2, 8, 4), (3, 5, 5), (8, 4, 4), (2, 2, 4), (1, 6, 5),
+                                               (4, 3, 4), (4, 7, 4), (6, 2, 4), (6, 5, 4), (8, 1, 4), (8, 8, 4), (5, 4, 4), (2, 5, 4), (2, 7, 3)])
 def test_oracle_matches_reference_c_decoder(oracle, channels, bits, sfb):
     """CBR decode of the restatement == the reference's own c/sea.h (frames multiple of scale_factor_frames, c/sea.h:168)."""
     if not oracle.have_ref():
