@@ -227,15 +227,26 @@ struct LutTag {
     static constexpr int value = M;
 };
 
-template <bool V>
-struct NarrowTag {
-    static constexpr bool value = V;
+// How a trial accumulates the weights penalty of lms.rs:53-62 (all three are exact; the guards are per block and warp-uniform):
+//   kRankWide    any weights: 64-bit sum of squares, 64-bit shift, 64x64 square;
+//   kRankNarrow  every |w| < 2^23 during the block: the shifted sum fits 31 bits, one 32x32->64 multiply-add;
+//   kRankSum32   sum_i (|w_i| + F * max|delta|)^2 < 2^32 at the start of a 20-frame block: sum w^2 stays below 2^32 for the whole
+//                block, so it is four 32-bit multiply-adds, the penalty root is <= (2^32 >> 18) - 0x8ff = 14081 and twenty squares
+//                of it fit one 32-bit accumulator (20 * 14081^2 < 2^32) that joins the 64-bit rank after the block.  IMAD.WIDE
+//                costs the FMA pipe 4 clocks against 2 for IMAD (profiles/r01_int_ops_ubench.txt), and that pipe bounds this
+//                kernel wherever two warps share a sub-partition: 20 of its 52 clocks per step were these five wide multiplies.
+enum : int { kRankWide = 0, kRankNarrow = 1, kRankSum32 = 2 };
+template <int V>
+struct RankTag {
+    static constexpr int value = V;
 };
 
 struct FastLut {
     const int32_t *lut;     // shared memory: per size a table [code][32 lanes] (lane & 15 = scale factor)
     const int32_t *recip;   // shared memory: [slot][16]
-    uint32_t slot_off[4];   // word offset of the table of size lo_size + i
+    // word offset of the table of `size` in [code][32] units: sum of 32 << z over lo_size <= z < size = (32 << size) - (32 << lo_size)
+    // (arithmetic, not an array: a runtime index into this struct put it on the stack -- one LDL per block, 4 % of the VBR profile)
+    __device__ __forceinline__ uint32_t slot_off(uint32_t size) const { return (32u << size) - (32u << lo_size); }
     uint32_t lo_size;
     int mode;               // kEncLut32 / kEncLut16 / kEncLutGlobal
 };
@@ -322,7 +333,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const int32_t recip = fl.recip[slot * 16u + sf];
             // shared [code][lane] / [code][sf] (two chains share a row) / global [sf][code]: see kEncLut*
             const int32_t *row = fl.mode == kEncLutGlobal ? tab + tab_dqt_off(4, size) + (sf << size)
-                                                          : fl.lut + (fl.mode == kEncLut32 ? fl.slot_off[slot] + lane : (fl.slot_off[slot] >> 1) + sf);
+                                                          : fl.lut + (fl.mode == kEncLut32 ? fl.slot_off(size) + lane : (fl.slot_off(size) >> 1) + sf);
             const uint32_t kmax = (1u << (size - 1u)) - 1u;
 
             // every candidate starts from the chain's state (kept in registers: the winner broadcasts it at the end of the block)
@@ -338,9 +349,11 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const int16_t *xs = xbuf + grp * F;
             uint8_t *cbuf = codes + warp * (F * 32u) + lane;  // [frame][lane] per warp: constant stride, immediate offsets when unrolled
             // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
-            auto trial = [&](auto narrow_tag, auto lut_tag) {
-                constexpr bool kNarrow = decltype(narrow_tag)::value;
+            uint32_t pen32 = 0;  // kRankSum32: the block's penalties
+            auto trial = [&](auto rank_tag, auto lut_tag, auto unrolled_tag) {
+                constexpr int kRank = decltype(rank_tag)::value;
                 constexpr int kMode = decltype(lut_tag)::value;
+                constexpr bool kUnrolled = decltype(unrolled_tag)::value != 0;
                 auto step = [&](uint32_t f) {
                     const int32_t xv = xs[f];
                     // lms.rs:33-41 as a two-level sum (wrapping adds associate): the newest history value enters last
@@ -389,7 +402,16 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     }
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
                     const int32_t y = clamp_i16(v);
-                    rank = rank_step<kNarrow>(rank, xv - y, w);
+                    if (kRank == kRankSum32) {
+                        const uint32_t sum = (uint32_t)w[0] * (uint32_t)w[0] + (uint32_t)w[1] * (uint32_t)w[1] +
+                                             (uint32_t)w[2] * (uint32_t)w[2] + (uint32_t)w[3] * (uint32_t)w[3];
+                        const uint32_t t = (uint32_t)__viaddmax_s32((int32_t)(sum >> 18), -0x8ff, 0);
+                        pen32 += t * t;
+                        const int32_t e = xv - y;
+                        rank += (unsigned long long)((long long)e * (long long)e);
+                    } else {
+                        rank = rank_step<kRank == kRankNarrow>(rank, xv - y, w);
+                    }
                     const int32_t delta = d >> 4;  // lms.rs:43-51
 #pragma unroll
                     for (int i = 0; i < 4; i++) w[i] += delta * sg[i];
@@ -397,7 +419,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (v >> 31) | 1;  // the clamp keeps the sign
                     cbuf[f * 32u] = (uint8_t)code;
                 };
-                if (nf == 20u) {  // the default block: fully unrolled (immediate offsets, no loop control, penalties of one step
+                if (kUnrolled) {  // the default block: fully unrolled (immediate offsets, no loop control, penalties of one step
                                   // scheduled into the table-load shadow of the next)
 #pragma unroll
                     for (uint32_t f = 0; f < 20u; f++) step(f);
@@ -406,10 +428,32 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     for (uint32_t f = 0; f < nf; f++) step(f);
                 }
             };
+            // per-block guards of the penalty forms (warp-uniform: one code path per block)
             const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
+            bool sum32 = false;
+            if (nf == 20u) {
+                // a weight moves by |d >> 4| <= (top magnitude + 15) >> 4 per frame (lms.rs:43-51); top magnitude = the row's last even code
+                int32_t top;
+                if (kDirect) top = mag[kLevels];
+                else if (fl.mode == kEncLutGlobal) top = __ldg(row + 2u * kmax);
+                else top = row[(2u * kmax) << (fl.mode == kEncLut32 ? 5 : 4)];
+                const uint32_t grow = 20u * (((uint32_t)top + 15u) >> 4);
+                unsigned long long g = 0;
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t a = (w[i] < 0 ? 0u - (uint32_t)w[i] : (uint32_t)w[i]) + grow;  // <= 2^31 + 20 * 1600
+                    ok &= a < 65536u;
+                    g += (unsigned long long)a * a;  // meaningful only while ok: four terms below 2^32
+                }
+                sum32 = __all_sync(0xffffffffu, ok && (g >> 32) == 0ull);
+            }
             auto run = [&](auto lut_tag) {
-                if (narrow) trial(NarrowTag<true>{}, lut_tag);
-                else trial(NarrowTag<false>{}, lut_tag);
+                if (sum32) trial(RankTag<kRankSum32>{}, lut_tag, LutTag<1>{});
+                else if (narrow && nf == 20u) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<1>{});
+                else if (narrow) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<0>{});
+                else trial(RankTag<kRankWide>{}, lut_tag, LutTag<0>{});
+                rank += pen32;
             };
             if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1)>{});
             else if (fl.mode == kEncLut32) run(LutTag<kEncLut32>{});
@@ -515,6 +559,69 @@ __device__ void bitonic_sort(unsigned long long *keys, uint32_t *idx, uint32_t n
     }
 }
 
+// The same sort for the default shape (one warp per CTA, at most 512 items -- stereo chunks of 256 blocks) held in registers:
+// element e = r * 32 + lane lives in register r of its lane, so a compare-exchange at distance j < 32 is a shuffle and at
+// j >= 32 an exchange between two registers of one lane.  (rank, idx) packs into one 64-bit key while every rank is below 2^55;
+// returns false (nothing written) otherwise and the caller takes the shared-memory sort.  The shared-memory version cost 19 k
+// instructions per chunk, most of them waiting on generic loads (8 % of the VBR-3 profile); this one is ~6 k with 16-way ILP.
+__device__ bool warp_sort_512(unsigned long long *keys, uint32_t *idx, uint32_t n, uint32_t np2)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long v[16];
+    bool fits = true;
+#pragma unroll
+    for (uint32_t r = 0; r < 16u; r++) {
+        const uint32_t e = r * 32u + lane;
+        const unsigned long long k = e < n ? keys[e] : 0ull;
+        fits &= (k >> 55) == 0ull;
+        v[r] = e < n ? (k << 9) | e : ~0ull;
+    }
+    if (!__all_sync(0xffffffffu, fits)) return false;
+    for (uint32_t k = 2; k <= 512u; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32u) {
+                auto exchange = [&](auto jr_tag) {
+                    constexpr uint32_t jr = decltype(jr_tag)::value;
+#pragma unroll
+                    for (uint32_t r = 0; r < 16u; r++) {
+                        if (r & jr) continue;
+                        const bool up = ((r << 5) & k) == 0u;  // k >= 64: the direction depends on the register index only
+                        const unsigned long long a = v[r], b = v[r | jr];
+                        const bool swap = (a > b) == up;
+                        v[r] = swap ? b : a;
+                        v[r | jr] = swap ? a : b;
+                    }
+                };
+                switch (j >> 5) {
+                    case 1: exchange(LutTag<1>{}); break;
+                    case 2: exchange(LutTag<2>{}); break;
+                    case 4: exchange(LutTag<4>{}); break;
+                    default: exchange(LutTag<8>{}); break;
+                }
+            } else {
+                const bool lower = (lane & j) == 0u;
+#pragma unroll
+                for (uint32_t r = 0; r < 16u; r++) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (((r << 5) | lane) & k) == 0u;
+                    const bool take_min = lower == up;
+                    v[r] = ((other < v[r]) == take_min) ? other : v[r];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < 16u; r++) {
+        const uint32_t e = r * 32u + lane;
+        if (e < np2) {
+            keys[e] = e < n ? v[r] >> 9 : ~0ull;
+            idx[e] = e < n ? (uint32_t)v[r] & 511u : 0xffffffffu;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
 // FB = -1: generic search pass (any scale_factor_bits);  FB = 0: fast pass, runtime residual sizes (VBR);  FB = 1..8: fast pass, CBR.
 template <int FB>
 __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const EncStream *__restrict__ streams,
@@ -553,7 +660,6 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
         uint32_t off = 0;
         for (uint32_t i = 0; i < n_slots; i++) {
             const uint32_t size = fl.lo_size + i;
-            fl.slot_off[i] = off;
             if (size <= 8u) {
                 for (uint32_t e = tid; e < 16u; e += T) rcp[i * 16u + e] = tab[tab_recip_off(4, size) + e];
                 if (fl.mode == kEncLut32) {
@@ -660,7 +766,7 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
             }
             for (uint32_t i = tid; i < items; i += T) vs.sizes[i] = (uint8_t)p.base;
             __syncthreads();
-            bitonic_sort(vs.keys, vs.idx, np2);
+            if (!(T == 32u && np2 <= 512u && warp_sort_512(vs.keys, vs.idx, sortable, np2))) bitonic_sort(vs.keys, vs.idx, np2);
             for (uint32_t pos = tid; pos < sortable; pos += T) {
                 uint32_t size = p.base;
                 if (pos < m1) size = p.base - 1u;
@@ -678,7 +784,32 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
                 }
             }
             __syncthreads();
-            if (tid == 0) {  // bit offset of every block inside the residual section
+            if (T == 32u) {  // bit offset of every block inside the residual section: a run of blocks per lane, then a warp scan
+                const uint32_t per = (nblk + 31u) / 32u, b0 = tid * per, b1 = b0 + per < nblk ? b0 + per : nblk;
+                uint32_t mine = 0;
+                for (uint32_t blk = b0; blk < b1; blk++) {
+                    uint32_t rb = 0;
+                    for (uint32_t c = 0; c < C; c++) rb += vs.sizes[blk * C + c];
+                    uint32_t nf = frames - blk * F;
+                    if (nf > F) nf = F;
+                    vs.rowbits[blk] = rb;
+                    mine += nf * rb;
+                }
+                uint32_t incl = mine;
+#pragma unroll
+                for (uint32_t o = 1; o < 32u; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += up;
+                }
+                uint32_t acc = incl - mine;
+                for (uint32_t blk = b0; blk < b1; blk++) {
+                    uint32_t nf = frames - blk * F;
+                    if (nf > F) nf = F;
+                    vs.blkbit[blk] = acc;
+                    acc += nf * vs.rowbits[blk];
+                }
+                if (tid == 31u) sh_res_bits = incl;
+            } else if (tid == 0) {
                 uint32_t acc = 0;
                 for (uint32_t blk = 0; blk < nblk; blk++) {
                     uint32_t rb = 0;
