@@ -295,21 +295,33 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
         // k >= j  <=>  |n| >= m_j (m_j = 2j; size 2: 3) with n = (r*recip + 2^15) >> 16:
         //   r >= 0: r >= ceil(X/recip),  r < 0: |r| >= floor(X/recip) + 1,  X = 65536*m_j - 32768;
         // both in one unsigned compare A >= 2*ceil(X/recip) - 1 + [recip divides X] (A is even for r >= 0, odd for r < 0).
+        // VBR (FB == 0): the sizes change per block, so the thresholds and magnitudes of sizes 1..3 are prepared once per pass and a
+        // block whose two chains both have a size <= 3 selects its set (a size below 3 leaves the unused thresholds at "never").
         constexpr bool kDirect = FB >= 1 && FB <= 3;
-        constexpr int kLevels = FB == 3 ? 3 : (FB == 2 ? 1 : 0);
+        constexpr int kLevels = FB == 0 ? 3 : (FB == 3 ? 3 : (FB == 2 ? 1 : 0));
         uint32_t theta[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
         int32_t mag[4] = {0, 0, 0, 0};
-        if (kDirect) {
-            const uint32_t rc = (uint32_t)fl.recip[sf];
-            const int32_t *row0 = tab + tab_dqt_off(4, FB > 0 ? FB : 1) + (sf << (FB > 0 ? FB : 1));
+        uint32_t theta_by[3][3] = {{0xffffffffu, 0xffffffffu, 0xffffffffu}, {0xffffffffu, 0xffffffffu, 0xffffffffu}, {0xffffffffu, 0xffffffffu, 0xffffffffu}};
+        int32_t mag_by[3][4] = {};  // [size - 1][level]
+        auto direct_setup = [&](uint32_t z, uint32_t rc, uint32_t *th, int32_t *mg) {
+            const uint32_t levels = z == 3u ? 3u : (z == 2u ? 1u : 0u);
+            const int32_t *row0 = tab + tab_dqt_off(4, z) + (sf << z);
 #pragma unroll
-            for (int j = 0; j <= kLevels; j++) mag[j] = __ldg(row0 + 2 * j);  // dqt[sf][2k] = +round(sf * curve[k]) (dqt.rs:114-123)
+            for (uint32_t j = 0; j < 4u; j++)
+                if (j <= levels) mg[j] = __ldg(row0 + 2u * j);  // dqt[sf][2k] = +round(sf * curve[k]) (dqt.rs:114-123)
 #pragma unroll
-            for (int j = 1; j <= kLevels; j++) {
-                const uint32_t m = FB == 2 ? 3u : 2u * (uint32_t)j;
-                const uint32_t X = 65536u * m - 32768u, q = X / rc, rem = X - q * rc;
-                theta[j - 1] = rem ? 2u * (q + 1u) - 1u : 2u * q;  // 2*ceil - 1 + [divides]
-            }
+            for (uint32_t j = 1; j < 4u; j++)
+                if (j <= levels) {
+                    const uint32_t m = z == 2u ? 3u : 2u * j;
+                    const uint32_t X = 65536u * m - 32768u, q = X / rc, rem = X - q * rc;
+                    th[j - 1u] = rem ? 2u * (q + 1u) - 1u : 2u * q;  // 2*ceil - 1 + [divides]
+                }
+        };
+        if (kDirect) direct_setup(FB > 0 ? FB : 1, (uint32_t)fl.recip[sf], theta, mag);
+        if (FB == 0) {
+#pragma unroll
+            for (uint32_t z = 1; z <= 3u; z++)
+                if (z >= fl.lo_size && z <= fl.lo_size + 3u) direct_setup(z, (uint32_t)fl.recip[(z - fl.lo_size) * 16u + sf], theta_by[z - 1u], mag_by[z - 1u]);
         }
         for (uint32_t blk = 0; blk < nblk; blk++) {
             uint32_t nf = frames - blk * F;
@@ -349,11 +361,26 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const int16_t *xs = xbuf + grp * F;
             uint8_t *cbuf = codes + warp * (F * 32u) + lane;  // [frame][lane] per warp: constant stride, immediate offsets when unrolled
             // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
+            bool direct_now = kDirect;
+            if (FB == 0) {
+                direct_now = __all_sync(0xffffffffu, size <= 3u);
+                if (direct_now) {
+                    const bool z3 = size == 3u, z2 = size == 2u;
+                    theta[0] = z3 ? theta_by[2][0] : (z2 ? theta_by[1][0] : 0xffffffffu);
+                    theta[1] = z3 ? theta_by[2][1] : 0xffffffffu;
+                    theta[2] = z3 ? theta_by[2][2] : 0xffffffffu;
+                    mag[0] = z3 ? mag_by[2][0] : (z2 ? mag_by[1][0] : mag_by[0][0]);
+                    mag[1] = z3 ? mag_by[2][1] : mag_by[1][1];
+                    mag[2] = mag_by[2][2];
+                    mag[3] = mag_by[2][3];
+                }
+            }
             uint32_t pen32 = 0;  // kRankSum32: the block's penalties
-            auto trial = [&](auto rank_tag, auto lut_tag, auto unrolled_tag) {
+            auto trial = [&](auto rank_tag, auto lut_tag, auto unrolled_tag, auto direct_tag) {
                 constexpr int kRank = decltype(rank_tag)::value;
                 constexpr int kMode = decltype(lut_tag)::value;
                 constexpr bool kUnrolled = decltype(unrolled_tag)::value != 0;
+                constexpr bool kDir = decltype(direct_tag)::value != 0;
                 auto step = [&](uint32_t f) {
                     const int32_t xv = xs[f];
                     // lms.rs:33-41 as a two-level sum (wrapping adds associate): the newest history value enters last
@@ -363,7 +390,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     const int32_t r = (int32_t)((uint32_t)xv - (uint32_t)pr);
                     uint32_t code;
                     int32_t d;
-                    if (kDirect) {
+                    if (kDir) {
                         const int32_t ms = r >> 31;                                      // 0 / -1
                         const uint32_t A = ((uint32_t)r << 1) ^ (uint32_t)ms;            // 2|r| - (r < 0)
                         int32_t mg = mag[0];
@@ -419,9 +446,16 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (v >> 31) | 1;  // the clamp keeps the sign
                     cbuf[f * 32u] = (uint8_t)code;
                 };
-                if (kUnrolled) {  // the default block: fully unrolled (immediate offsets, no loop control, penalties of one step
-                                  // scheduled into the table-load shadow of the next)
+                if (kUnrolled && FB > 0) {  // the default block: fully unrolled (immediate offsets, no loop control, penalties of one
+                                            // step scheduled into the table-load shadow of the next)
 #pragma unroll
+                    for (uint32_t f = 0; f < 20u; f++) step(f);
+                } else if (kUnrolled) {
+                    // VBR: the blocks of a chunk alternate between several forms of the trial (direct / table, 32-bit / 64-bit
+                    // penalty) and the CTAs of an SM sit in different passes: fully unrolled (13 KB each) the hot forms overflow
+                    // the 32 KB instruction cache (VBR-4 ran at half speed).  Four steps per iteration keep the register rotation of
+                    // the history free and the forms at 2.5 KB each.
+#pragma unroll 4
                     for (uint32_t f = 0; f < 20u; f++) step(f);
                 } else {
 #pragma unroll 4
@@ -435,6 +469,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 // a weight moves by |d >> 4| <= (top magnitude + 15) >> 4 per frame (lms.rs:43-51); top magnitude = the row's last even code
                 int32_t top;
                 if (kDirect) top = mag[kLevels];
+                else if (FB == 0 && direct_now) top = size == 3u ? mag[3] : (size == 2u ? mag[1] : mag[0]);
                 else if (fl.mode == kEncLutGlobal) top = __ldg(row + 2u * kmax);
                 else top = row[(2u * kmax) << (fl.mode == kEncLut32 ? 5 : 4)];
                 const uint32_t grow = 20u * (((uint32_t)top + 15u) >> 4);
@@ -448,17 +483,18 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 }
                 sum32 = __all_sync(0xffffffffu, ok && (g >> 32) == 0ull);
             }
-            auto run = [&](auto lut_tag) {
-                if (sum32) trial(RankTag<kRankSum32>{}, lut_tag, LutTag<1>{});
-                else if (narrow && nf == 20u) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<1>{});
-                else if (narrow) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<0>{});
-                else trial(RankTag<kRankWide>{}, lut_tag, LutTag<0>{});
+            auto run = [&](auto lut_tag, auto direct_tag) {
+                if (sum32) trial(RankTag<kRankSum32>{}, lut_tag, LutTag<1>{}, direct_tag);
+                else if (narrow && nf == 20u) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<1>{}, direct_tag);
+                else if (narrow) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<0>{}, direct_tag);
+                else trial(RankTag<kRankWide>{}, lut_tag, LutTag<0>{}, direct_tag);
                 rank += pen32;
             };
-            if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1)>{});
-            else if (fl.mode == kEncLut32) run(LutTag<kEncLut32>{});
-            else if (fl.mode == kEncLut16) run(LutTag<kEncLut16>{});
-            else run(LutTag<kEncLutGlobal>{});
+            if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1)>{}, LutTag<kDirect ? 1 : 0>{});
+            else if (direct_now) run(LutTag<kEncLut32>{}, LutTag<1>{});  // no table on this path
+            else if (fl.mode == kEncLut32) run(LutTag<kEncLut32>{}, LutTag<0>{});
+            else if (fl.mode == kEncLut16) run(LutTag<kEncLut16>{}, LutTag<0>{});
+            else run(LutTag<kEncLutGlobal>{}, LutTag<0>{});
             // arg-min over the 16 candidates of the chain: strict total order (rank, ord); ord follows from the lane.  (Three
             // REDUX min-reductions -- high word, low word, order -- need a third of the instructions but measured 5 % slower at
             // 1024 streams: their latency sits on the per-block critical path of a latency-bound kernel.)
@@ -703,6 +739,8 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
     }
     __syncthreads();
 
+    // the host picks FB > 0 for CBR and FB = 0 for VBR (launch_encode_generic): only the generic kernel carries both branches
+    const bool vbr = FB > 0 ? false : (FB == 0 ? true : p.vbr != 0);
     const uint32_t n_chunks = div_ceil_u32(st.n_frames, N);
     uint64_t written = p.raw_chunk_mode ? 0 : kFileHeaderBytes;
     uint32_t first_chunk_bytes = 0;
@@ -740,7 +778,7 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
             put_byte(chunk_sh, base_byte + 8u + 2u * t + 1u, wv >> 8);
         }
 
-        if (!p.vbr) {
+        if (!vbr) {
             if (FB >= 0) search_pass_fast<FB>(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
             else search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
             if (tid == 0) sh_res_bits = frames * C * p.hdr_bits;
