@@ -243,6 +243,7 @@ struct RankTag {
 
 struct FastLut {
     const int32_t *lut;     // shared memory: per size a table [code][32 lanes] (lane & 15 = scale factor)
+    uint32_t lut_sh;        // the same as a shared-window address
     const int32_t *recip;   // shared memory: [slot][16]
     // word offset of the table of `size` in [code][32] units: sum of 32 << z over lo_size <= z < size = (32 << size) - (32 << lo_size)
     // (arithmetic, not an array: a runtime index into this struct put it on the stack -- one LDL per block, 4 % of the VBR profile)
@@ -318,6 +319,12 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 }
         };
         if (kDirect) direct_setup(FB > 0 ? FB : 1, (uint32_t)fl.recip[sf], theta, mag);
+        int32_t top_by[4] = {0, 0, 0, 0};  // largest magnitude of the lane's row per table slot (bounds the weight drift of a block)
+#pragma unroll
+        for (uint32_t i = 0; i < (FB > 0 ? 1u : 4u); i++) {
+            const uint32_t z = fl.lo_size + i;
+            if (z <= 8u) top_by[i] = __ldg(tab + tab_dqt_off(4, z) + (sf << z) + (1u << z) - 2u);
+        }
         if (FB == 0) {
 #pragma unroll
             for (uint32_t z = 1; z <= 3u; z++)
@@ -344,8 +351,10 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const uint32_t slot = FB > 0 ? 0u : size - fl.lo_size;
             const int32_t recip = fl.recip[slot * 16u + sf];
             // shared [code][lane] / [code][sf] (two chains share a row) / global [sf][code]: see kEncLut*
-            const int32_t *row = fl.mode == kEncLutGlobal ? tab + tab_dqt_off(4, size) + (sf << size)
-                                                          : fl.lut + (fl.mode == kEncLut32 ? fl.slot_off(size) + lane : (fl.slot_off(size) >> 1) + sf);
+            // Two separate views: a global pointer and a 32-bit shared-window address.  (One pointer selected between the two
+            // made the VBR kernel's table reads generic LD.E -- long-scoreboard latency on the step's critical path.)
+            const int32_t *row = tab + tab_dqt_off(4, size) + (sf << size);
+            const uint32_t row_sh = fl.lut_sh + 4u * (fl.mode == kEncLut32 ? fl.slot_off(size) + lane : (fl.slot_off(size) >> 1) + sf);
             const uint32_t kmax = (1u << (size - 1u)) - 1u;
 
             // every candidate starts from the chain's state (kept in registers: the winner broadcasts it at the end of the block)
@@ -423,8 +432,8 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     if (kMode == kEncLutGlobal) {
                         d = __ldg(row + sbit + k2);
                     } else {
-                        const int32_t *rs = row + (sbit << (kMode == kEncLut32 ? 5 : 4));
-                        d = rs[k2 << (kMode == kEncLut32 ? 5 : 4)];
+                        const uint32_t rs = row_sh + (sbit << (kMode == kEncLut32 ? 7 : 6));
+                        asm("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(rs + (k2 << (kMode == kEncLut32 ? 7 : 6))));
                     }
                     }
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
@@ -470,8 +479,8 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 int32_t top;
                 if (kDirect) top = mag[kLevels];
                 else if (FB == 0 && direct_now) top = size == 3u ? mag[3] : (size == 2u ? mag[1] : mag[0]);
-                else if (fl.mode == kEncLutGlobal) top = __ldg(row + 2u * kmax);
-                else top = row[(2u * kmax) << (fl.mode == kEncLut32 ? 5 : 4)];
+                else top = top_by[0];
+                if (FB == 0 && !direct_now) top = slot == 0u ? top_by[0] : (slot == 1u ? top_by[1] : (slot == 2u ? top_by[2] : top_by[3]));
                 const uint32_t grow = 20u * (((uint32_t)top + 15u) >> 4);
                 unsigned long long g = 0;
                 bool ok = true;
@@ -689,6 +698,7 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
         int32_t *rcp = reinterpret_cast<int32_t *>(extra + (((T >> 5) * 2u * F * 2u + 15u) & ~15u));
         int32_t *lut = rcp + 64;
         fl.lut = lut;
+        fl.lut_sh = (uint32_t)__cvta_generic_to_shared(lut);
         fl.recip = rcp;
         fl.lo_size = FB > 0 ? (uint32_t)FB : (p.base > 1u ? p.base - 1u : 1u);
         fl.mode = FB > 0 ? enc_lut_mode_cbr(FB > 0 ? FB : 1) : (int)p.lut_mode;
@@ -948,12 +958,17 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     int lut_mode = kEncLut32;
     if (fast) {
         smem += ((size_t)warps * 2u * p.F * 2u + 15u) & ~(size_t)15u;
-        {   // ~7 CTAs (streams) per SM at the benchmark's 1024 streams: keep the CTA at or under 28 KB where possible
+        {   // One CTA per stream, all of them resident at once if they fit: with k = ceil(streams / 148) CTAs per SM a CTA may use
+            // 227 KB / k less the 1 KB the hardware reserves per CTA (31 KB at the benchmark's 1024 streams); with more streams
+            // than that would leave 28 KB for, keep the CTA at or under 28 KB (8 per SM, several waves).
             const int fb = p.vbr ? 0 : (int)p.hdr_bits;
             const size_t e = enc_lut_entries(fb, p.base), other = smem + 256u + (p.vbr ? (size_t)enc_vbr_scratch_bytes(p) + 16u : 0u);
+            const size_t per_sm = (p.n_streams + 147u) / 148u;
+            size_t budget = 227u * 1024u / per_sm;
+            budget = budget > 1280u + 28u * 1024u ? budget - 1280u : 28u * 1024u;
             if (!p.vbr) lut_mode = enc_lut_mode_cbr(fb);
-            else if (other + e * 128u <= 28u * 1024u) lut_mode = kEncLut32;
-            else if (other + e * 64u <= 28u * 1024u) lut_mode = kEncLut16;
+            else if (other + e * 128u <= budget) lut_mode = kEncLut32;
+            else if (other + e * 64u <= budget) lut_mode = kEncLut16;
             else lut_mode = kEncLutGlobal;
             if (lut_mode != kEncLutGlobal) smem += e * (lut_mode == kEncLut32 ? 128u : 64u);
         }
