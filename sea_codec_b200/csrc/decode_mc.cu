@@ -50,13 +50,36 @@ __device__ __forceinline__ uint32_t find_stream_m(const DecStream *streams, uint
     return lo;
 }
 
+template <int V>
+struct ParTag {
+    static constexpr int value = V;
+};
+
 template <int CT, int B>
 struct MCfg {
     static constexpr int F = 20;
-    static constexpr int CPL = (CT % 4 == 0) ? 4 : 2;   // channels per lane: a quad where the count allows (fewer memory instructions per sample)
+#ifndef SEA_MC_WHOLE
+#define SEA_MC_WHOLE 1
+#endif
+    // Channels per lane.  SEA_MC_WHOLE (default): all of them -- the lane owns whole frames, so its PCM goes out as full 16/32-byte
+    // stores (a pair or a quad per lane wrote 4/8 bytes to 32 different rows per instruction: the L1 tag stage, not the math,
+    // bounded 6 channels at 0.67 and 8 at 0.93 Tsamples/s) and CT independent LMS chains give the lane its ILP.  Otherwise a quad
+    // where the count allows, else a pair (the first version of this kernel).
+    static constexpr int CPL = SEA_MC_WHOLE ? CT : ((CT % 4 == 0) ? 4 : 2);
     static constexpr int U = CT / CPL;                  // lanes per chunk
-    static constexpr int kChunksPerWarp = 32 / U;       // CT = 6: 10 chunks, two idle lanes
-    static constexpr int HF = CT >= 6 ? 10 : 20;        // frames per looped body (divides F)
+    static constexpr int kChunksPerWarp = 32 / U;       // pairs of CT = 6: 10 chunks, two idle lanes
+    // frames per looped body (divides F): bounded by the window registers (body bits / 32) and, for whole frames, a body must
+    // be a whole number of stores
+#ifndef SEA_MC_HF8
+#define SEA_MC_HF8 10
+#endif
+    static constexpr int HF = CPL != CT ? (CT >= 6 ? 10 : 20) : (CT == 4 ? 20 : (CT == 6 ? 4 : (B <= 4 ? SEA_MC_HF8 : 4)));
+    static constexpr int WPF = CT / 2;                  // 32-bit words per frame
+    // Whole frames go out as 32-byte stores.  A body of 6 channels is an odd number of 16-byte halves (240 or 48 bytes), so its
+    // bodies alternate between two store phases (kPhaseWords = 4): the last four words of an even body wait in registers for
+    // the first four of the odd one.  The host only sends 6-channel batches here when N % 40 == 0 (even body count, 32-byte rows).
+    static constexpr int kPhaseWords = (HF * WPF) % 8;
+    static_assert(CPL != CT || kPhaseWords == 0 || kPhaseWords == 4, "a body must be a whole number of 16-byte halves");
     static constexpr int kBodyBits = HF * CT * B;       // bits of the stream one body walks through
     static constexpr int kNW = (kBodyBits - (CT - CPL) * B + 31 + 31) / 32;  // window words from my first field to my last (any phase)
     static constexpr int kBodyBytesMax = (kBodyBits + 7) / 8 + 1;
@@ -69,7 +92,10 @@ struct MCfg {
     static constexpr int kKeep = kAhead < 1 ? 1 : (kAhead > 4 ? 4 : kAhead);
     static constexpr int kPitch = 256 + 16;
     static constexpr int kWarpBytes = 32 * kPitch + 64;
-    static constexpr int kWarps = CT == 4 ? 16 : 12;    // measured: 4 channels 2.14 ms at 16 warps (2.46 at 12); 8 channels 7.36 ms at 12 (8.75 at 16)
+#ifndef SEA_MC_WARPS8
+#define SEA_MC_WARPS8 12
+#endif
+    static constexpr int kWarps = CT == 4 ? 16 : (CPL == CT ? SEA_MC_WARPS8 : 12);  // measured: 4 channels 2.14 ms at 16 warps (2.46 at 12); quads of 8: 7.36 ms at 12 (8.75 at 16)
     static_assert(2 * kBodyBytesMax + 32 <= 256, "ring too small for two bodies");
 };
 
@@ -140,11 +166,16 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     // scale-factor nibbles of a block for my channels, first channel in the top nibble of the CPL*4-bit value
     auto load_sf = [&](uint32_t blk) -> uint32_t {
         const uint8_t *q = sfp + (size_t)blk * (CT / 2);
-        return CPL == 4 ? ((uint32_t)__ldg(q) << 8) | (uint32_t)__ldg(q + 1) : (uint32_t)__ldg(q);
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < CPL / 2; j++) v = (v << 8) | (uint32_t)__ldg(q + j);
+        return v;
     };
     uint32_t sfb = load_sf(0);
 
-    for (uint32_t bd = 0; bd < n_bodies; bd++) {
+    uint32_t ow[8];  // whole frames: the 32-byte store being assembled (carried across bodies when kPhaseWords != 0)
+    auto body = [&](uint32_t bd, auto parity_tag) {
+        constexpr int kPar = decltype(parity_tag)::value;
         // ---- top the ring up, then wait for everything but that (the bytes of this body were issued a body ago)
         {
             const uint32_t wq = posg >> 5;
@@ -176,19 +207,27 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
         posg += Cfg::kBodyBits;
 
         uint8_t *ob = out + (size_t)bd * (Cfg::HF * CT * 2);
-        uint32_t ow[8];  // U == 1: four frames being assembled into one 32-byte store
 #pragma unroll
         for (int fi = 0; fi < Cfg::HF; fi++) {
             constexpr int kGB = CPL * B;
             const int bit = fi * CT * B;  // compile-time position of my group of codes in W[]
             const int wd = bit >> 5, off = bit & 31;
-            uint32_t x;  // my CPL codes in the low CPL*B bits, first channel highest
-            if (off + kGB <= 32) x = W[wd] >> (32 - off - kGB);
-            else x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - kGB) & 31);
+            uint32_t x = 0;  // my CPL codes in the low CPL*B bits, first channel highest (groups of up to 32 bits)
+            if (kGB <= 32) {
+                if (off + kGB <= 32) x = W[wd] >> (32 - off - kGB);
+                else x = __funnelshift_r(W[wd + 1], W[wd], (64 - off - kGB) & 31);
+            }
             int32_t y[CPL], d[CPL], sgn[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; c++) {
-                const uint32_t code = (x >> (B * (CPL - 1 - c))) & ((1u << B) - 1u);
+                uint32_t code;
+                if (kGB <= 32) {
+                    code = (x >> (B * (CPL - 1 - c))) & ((1u << B) - 1u);
+                } else {  // wider groups: every field on its own, still at a compile-time position
+                    const int cb = bit + c * B, cw = cb >> 5, co = cb & 31;
+                    if (co + B <= 32) code = (W[cw] >> (32 - co - B)) & ((1u << B) - 1u);
+                    else code = __funnelshift_r(W[cw + 1], W[cw], (64 - co - B) & 31) & ((1u << B) - 1u);
+                }
                 d[c] = lds_s32m(rowbase[c] + code * 4u);
                 const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                      (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
@@ -213,20 +252,33 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
                 sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
             }
             if (Cfg::U == 1) {
-                // the lane owns whole frames (CT == CPL == 4): four consecutive frames are one 32-byte sector -> 256-bit stores, as
-                // in the stereo kernel (8-byte stores to 32 different rows per instruction choked the L1 tag stage: 26 % issue)
-                ow[(fi & 3) * 2] = packed[0];
-                ow[(fi & 3) * 2 + 1] = packed[CPL / 2 - 1];
-                if ((fi & 3) == 3 && valid) {
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ob + (fi >> 2) * 32), "r"(ow[0]), "r"(ow[1]),
-                                 "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
-                                 : "memory");
+                // the lane owns whole frames: consecutive frames fill 32-byte sectors -> 256-bit stores as in the stereo kernel
+                // (128-bit where a body is not a multiple of 32 bytes: 6 channels); 8-byte stores to 32 different rows per
+                // instruction choked the L1 tag stage (26 % issue)
+#pragma unroll
+                for (int q = 0; q < Cfg::WPF; q++) {
+                    const int widx = kPar * Cfg::kPhaseWords + fi * Cfg::WPF + q;  // word position counted from the last 32-byte boundary before the body
+                    ow[widx % 8] = packed[q];
+                    if (widx % 8 == 7 && valid) {
+                        uint8_t *dst = ob + (widx / 8) * 32 - kPar * Cfg::kPhaseWords * 4;
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]),
+                                     "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                                     : "memory");
+                    }
                 }
             } else if (valid) {
                 if (CPL == 4) *reinterpret_cast<uint2 *>(ob + fi * (CT * 2)) = make_uint2(packed[0], packed[CPL / 2 - 1]);
                 else *reinterpret_cast<uint32_t *>(ob + fi * (CT * 2)) = packed[0];
             }
         }
+    };
+    if (Cfg::U == 1 && Cfg::kPhaseWords != 0) {
+        for (uint32_t bd = 0; bd < n_bodies; bd += 2) {
+            body(bd, ParTag<0>{});
+            body(bd + 1u, ParTag<1>{});
+        }
+    } else {
+        for (uint32_t bd = 0; bd < n_bodies; bd++) body(bd, ParTag<0>{});
     }
 }
 
@@ -235,6 +287,7 @@ bool decode_mc_supported(const DecFastParams &p)
     if (p.channels != 4 && p.channels != 6 && p.channels != 8) return false;
     if ((p.hdr_word & 0xffu) != 1u) return false;  // CBR chunks only
     if (p.F != 20 || p.s != 4 || p.b < 1 || p.b > 8) return false;
+    if (p.channels == 6 && p.N % 40u != 0) return false;  // 12-byte frames: 32-byte rows and an even number of bodies (see MCfg)
     return p.N != 0 && p.N % 20u == 0;
 }
 
