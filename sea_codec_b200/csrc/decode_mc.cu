@@ -163,15 +163,25 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
 
     const uint32_t n_bodies = p.N / Cfg::HF;
     constexpr int kBodiesPerBlock = Cfg::F / Cfg::HF;
-    // scale-factor nibbles of a block for my channels, first channel in the top nibble of the CPL*4-bit value
-    auto load_sf = [&](uint32_t blk) -> uint32_t {
+    // scale-factor nibbles of a block for my channels, first channel in the top nibble of the CPL*4-bit value.  The bytes of the
+    // NEXT block are requested when a block starts and only combined when the next one does: consumed right after the load
+    // (the first version) every block waited out a global-memory round trip -- 22 % of the stall samples of
+    // profiles/r01_decode_mc_v3 sat on the shift behind that load.
+    uint32_t sf_raw[CPL / 2];
+    auto request_sf = [&](uint32_t blk) {
         const uint8_t *q = sfp + (size_t)blk * (CT / 2);
+#pragma unroll
+        for (int j = 0; j < CPL / 2; j++) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(sf_raw[j]) : "l"(q + j));
+    };
+    auto combine_sf = [&]() -> uint32_t {
         uint32_t v = 0;
 #pragma unroll
-        for (int j = 0; j < CPL / 2; j++) v = (v << 8) | (uint32_t)__ldg(q + j);
+        for (int j = 0; j < CPL / 2; j++) v = (v << 8) | sf_raw[j];
         return v;
     };
-    uint32_t sfb = load_sf(0);
+    request_sf(0);
+    uint32_t sf_cur = 0;
+    const uint32_t n_blocks = p.N / Cfg::F;
 
     uint32_t ow[8];  // whole frames: the 32-byte store being assembled (carried across bodies when kPhaseWords != 0)
     auto body = [&](uint32_t bd, auto parity_tag) {
@@ -189,9 +199,11 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
             cp_wait_keep<Cfg::kKeep>();
         }
         // scale factors of this body's block (one byte per block and pair); the next block's byte is fetched a body ahead
-        const uint32_t blk = bd / kBodiesPerBlock;
-        const uint32_t sf_cur = sfb;
-        if ((bd % kBodiesPerBlock) == kBodiesPerBlock - 1 && bd + 1 < n_bodies) sfb = load_sf(blk + 1u);
+        if ((bd % kBodiesPerBlock) == 0) {
+            const uint32_t blk = bd / kBodiesPerBlock;
+            sf_cur = combine_sf();
+            if (blk + 1u < n_blocks) request_sf(blk + 1u);
+        }
         uint32_t rowbase[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; c++) rowbase[c] = lut_sh + (((sf_cur >> (4 * (CPL - 1 - c))) & 15u) << (B + 2));
