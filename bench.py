@@ -488,5 +488,20 @@ def main():
     dist.shutdown()
 
 
+def _main_with_clean_stdout():
+    """stdout carries the one JSON line and nothing else: libraries that chat on fd 1 (NCCL prints its version banner there at
+    the first collective) are sent to stderr for the duration of the run."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = sys.stdout
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+    try:
+        main()
+    finally:
+        sys.stdout.flush()
+        sys.stdout = out
+
+
 if __name__ == "__main__":
-    main()
+    _main_with_clean_stdout()

@@ -31,9 +31,11 @@ def init(backend: str | None = None) -> RankInfo:
             os.environ.setdefault("MASTER_PORT", "29511")
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
+            kw = {}
             if backend == "nccl":
                 torch.cuda.set_device(info.local_rank)
-            dist.init_process_group(backend=backend, rank=info.rank, world_size=info.world)
+                kw["device_id"] = torch.device("cuda", info.local_rank)  # binds the communicator to this rank's GPU up front
+            dist.init_process_group(backend=backend, rank=info.rank, world_size=info.world, **kw)
     return info
 
 
