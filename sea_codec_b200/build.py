@@ -60,7 +60,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: 
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc(), "-shared", "-o", lib_path, *objs, "-cudart", "static"], check=True)
+    # the arch flag only keeps nvcc from assuming (and warning about) its default target at link time: the objects are sm_100a
+    subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path, *objs, "-cudart", "static"], check=True)
     return lib_path
 
 
