@@ -230,11 +230,17 @@ struct LutTag {
 // How a trial accumulates the weights penalty of lms.rs:53-62 (all three are exact; the guards are per block and warp-uniform):
 //   kRankWide    any weights: 64-bit sum of squares, 64-bit shift, 64x64 square;
 //   kRankNarrow  every |w| < 2^23 during the block: the shifted sum fits 31 bits, one 32x32->64 multiply-add;
-//   kRankSum32   sum_i (|w_i| + F * max|delta|)^2 < 2^32 at the start of a 20-frame block: sum w^2 stays below 2^32 for the whole
-//                block, so it is four 32-bit multiply-adds, the penalty root is <= (2^32 >> 18) - 0x8ff = 14081 and twenty squares
-//                of it fit one 32-bit accumulator (20 * 14081^2 < 2^32) that joins the 64-bit rank after the block.  IMAD.WIDE
-//                costs the FMA pipe 4 clocks against 2 for IMAD (profiles/r01_int_ops_ubench.txt), and that pipe bounds this
-//                kernel wherever two warps share a sub-partition: 20 of its 52 clocks per step were these five wide multiplies.
+//   kRankSum32   every |w_i| <= 32767 during a 20-frame block: sum w^2 < 2^32, so it is four 32-bit multiply-adds, the penalty
+//                root is <= (2^32 >> 18) - 0x8ff = 14081 and twenty squares of it fit one 32-bit accumulator (20 * 14081^2 < 2^32)
+//                that joins the 64-bit rank after the block.  IMAD.WIDE costs the FMA pipe 4 clocks against 2 for IMAD
+//                (profiles/r01_int_ops_ubench.txt), and that pipe bounds this kernel wherever two warps share a sub-partition:
+//                20 of its 52 clocks per step were these five wide multiplies.  The bound is checked AFTER the trial, from what
+//                the candidate actually did: a weight moves by |d >> 4| <= (|d| >> 4) + 1 per frame (lms.rs:43-51), so
+//                max|w(0)| + (sum|d| >> 4) + 20 <= 32767 proves it for every frame of the block; the trajectory (codes, history,
+//                weights) never depends on the penalty arithmetic, only the rank does, and a block whose proof fails in any lane is
+//                simply run again in the 64-bit form.  With the direct quantiser (sizes 1-3) the lane's largest magnitude is a
+//                register and the bound sum_i (|w_i| + 20 * max|delta|)^2 < 2^32 is taken before the trial instead (it holds
+//                at ordinary weights there and costs nothing per step; for the larger sizes it never held).
 enum : int { kRankWide = 0, kRankNarrow = 1, kRankSum32 = 2 };
 template <int V>
 struct RankTag {
@@ -250,6 +256,9 @@ struct FastLut {
     __device__ __forceinline__ uint32_t slot_off(uint32_t size) const { return (32u << size) - (32u << lo_size); }
     uint32_t lo_size;
     int mode;               // kEncLut32 / kEncLut16 / kEncLutGlobal
+#ifdef SEA_ENC_DEBUG_SPEC
+    unsigned long long *dbg;  // tuning builds: counts the 20-frame blocks that did NOT finish in the 32-bit penalty form
+#endif
 };
 
 template <int FB>
@@ -319,17 +328,12 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 }
         };
         if (kDirect) direct_setup(FB > 0 ? FB : 1, (uint32_t)fl.recip[sf], theta, mag);
-        int32_t top_by[4] = {0, 0, 0, 0};  // largest magnitude of the lane's row per table slot (bounds the weight drift of a block)
-#pragma unroll
-        for (uint32_t i = 0; i < (FB > 0 ? 1u : 4u); i++) {
-            const uint32_t z = fl.lo_size + i;
-            if (z <= 8u) top_by[i] = __ldg(tab + tab_dqt_off(4, z) + (sf << z) + (1u << z) - 2u);
-        }
         if (FB == 0) {
 #pragma unroll
             for (uint32_t z = 1; z <= 3u; z++)
                 if (z >= fl.lo_size && z <= fl.lo_size + 3u) direct_setup(z, (uint32_t)fl.recip[(z - fl.lo_size) * 16u + sf], theta_by[z - 1u], mag_by[z - 1u]);
         }
+        uint32_t spec_skip = 0;  // blocks left before the 32-bit penalty form is tried again after a failed proof
         for (uint32_t blk = 0; blk < nblk; blk++) {
             uint32_t nf = frames - blk * F;
             if (nf > F) nf = F;
@@ -384,7 +388,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     mag[3] = mag_by[2][3];
                 }
             }
-            uint32_t pen32 = 0;  // kRankSum32: the block's penalties
+            uint32_t pen32 = 0, dsum = 0;  // kRankSum32: the block's penalties and sum |d|
             auto trial = [&](auto rank_tag, auto lut_tag, auto unrolled_tag, auto direct_tag) {
                 constexpr int kRank = decltype(rank_tag)::value;
                 constexpr int kMode = decltype(lut_tag)::value;
@@ -435,6 +439,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                         const uint32_t rs = row_sh + (sbit << (kMode == kEncLut32 ? 7 : 6));
                         asm("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(rs + (k2 << (kMode == kEncLut32 ? 7 : 6))));
                     }
+                    if (kRank == kRankSum32) dsum = __sad(d, 0, dsum);  // + |d|
                     }
                     const int32_t v = (int32_t)((uint32_t)pr + (uint32_t)d);
                     const int32_t y = clamp_i16(v);
@@ -471,16 +476,19 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     for (uint32_t f = 0; f < nf; f++) step(f);
                 }
             };
-            // per-block guards of the penalty forms (warp-uniform: one code path per block)
+            // per-block choice of the penalty form (warp-uniform: one code path per block)
             const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
-            bool sum32 = false;
-            if (nf == 20u) {
-                // a weight moves by |d >> 4| <= (top magnitude + 15) >> 4 per frame (lms.rs:43-51); top magnitude = the row's last even code
-                int32_t top;
-                if (kDirect) top = mag[kLevels];
-                else if (FB == 0 && direct_now) top = size == 3u ? mag[3] : (size == 2u ? mag[1] : mag[0]);
-                else top = top_by[0];
-                if (FB == 0 && !direct_now) top = slot == 0u ? top_by[0] : (slot == 1u ? top_by[1] : (slot == 2u ? top_by[2] : top_by[3]));
+            uint32_t m0 = 0;  // max |w_i| at the start of the block (|INT_MIN| wraps to 2^31: never below the limit)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t a = w[i] < 0 ? 0u - (uint32_t)w[i] : (uint32_t)w[i];
+                m0 = a > m0 ? a : m0;
+            }
+            // direct quantiser: the lane's largest magnitude is in a register, so the bound is taken before the trial (no per-step
+            // bookkeeping): sum_i (|w_i| + 20 * max|delta|)^2 < 2^32 keeps sum w^2 below 2^32 for the whole block
+            bool prior32 = false;
+            if (nf == 20u && direct_now) {
+                const int32_t top = FB == 0 ? (size == 3u ? mag[3] : (size == 2u ? mag[1] : mag[0])) : mag[kLevels];
                 const uint32_t grow = 20u * (((uint32_t)top + 15u) >> 4);
                 unsigned long long g = 0;
                 bool ok = true;
@@ -490,14 +498,38 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     ok &= a < 65536u;
                     g += (unsigned long long)a * a;  // meaningful only while ok: four terms below 2^32
                 }
-                sum32 = __all_sync(0xffffffffu, ok && (g >> 32) == 0ull);
+                prior32 = __all_sync(0xffffffffu, ok && (g >> 32) == 0ull);
             }
+            // table quantiser: try the 32-bit form and prove it afterwards from sum |d| (see kRankSum32)
+            const bool try32 = nf == 20u && !direct_now && spec_skip == 0u && __all_sync(0xffffffffu, m0 < 30000u);
+            if (spec_skip) spec_skip--;
             auto run = [&](auto lut_tag, auto direct_tag) {
-                if (sum32) trial(RankTag<kRankSum32>{}, lut_tag, LutTag<1>{}, direct_tag);
-                else if (narrow && nf == 20u) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<1>{}, direct_tag);
+                if (prior32) {
+                    trial(RankTag<kRankSum32>{}, lut_tag, LutTag<1>{}, direct_tag);
+                    rank += pen32;
+                    return;
+                }
+                if (try32) {
+                    trial(RankTag<kRankSum32>{}, lut_tag, LutTag<1>{}, direct_tag);
+                    if (__all_sync(0xffffffffu, m0 + (dsum >> 4) + 20u <= 32767u)) {
+                        rank += pen32;
+                        return;
+                    }
+                    spec_skip = 8;  // the weights are running close to 2^15: leave the next blocks to the 64-bit form
+                    rank = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        w[i] = cw[i];
+                        h[i] = chh[i];
+                        sg[i] = (h[i] >> 31) | 1;
+                    }
+                }
+#ifdef SEA_ENC_DEBUG_SPEC
+                if (lane == 0 && nf == 20u) atomicAdd(fl.dbg, try32 ? (1ull << 20) : 1ull);  // failed proofs << 20 | not tried
+#endif
+                if (narrow && nf == 20u) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<1>{}, direct_tag);
                 else if (narrow) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<0>{}, direct_tag);
                 else trial(RankTag<kRankWide>{}, lut_tag, LutTag<0>{}, direct_tag);
-                rank += pen32;
             };
             if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1)>{}, LutTag<kDirect ? 1 : 0>{});
             else if (direct_now) run(LutTag<kEncLut32>{}, LutTag<1>{});  // no table on this path
@@ -699,6 +731,9 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
         int32_t *lut = rcp + 64;
         fl.lut = lut;
         fl.lut_sh = (uint32_t)__cvta_generic_to_shared(lut);
+#ifdef SEA_ENC_DEBUG_SPEC
+        fl.dbg = ties;
+#endif
         fl.recip = rcp;
         fl.lo_size = FB > 0 ? (uint32_t)FB : (p.base > 1u ? p.base - 1u : 1u);
         fl.mode = FB > 0 ? enc_lut_mode_cbr(FB > 0 ? FB : 1) : (int)p.lut_mode;
