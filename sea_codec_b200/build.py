@@ -41,9 +41,20 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: 
     """extra_flags / lib_path / build_dir: tuning builds (tools/build_variant.py) next to the product library."""
     if not force and not is_stale() and lib_path == LIB:
         return LIB
-    objs = []
     build_dir = build_dir or os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
+    # one builder at a time (several ranks of a torchrun job may find the library stale at once); whoever waited re-checks
+    import fcntl
+
+    with open(os.path.join(build_dir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale() and lib_path == LIB:
+            return LIB
+        return _build_locked(verbose, extra_flags, lib_path, build_dir)
+
+
+def _build_locked(verbose, extra_flags, lib_path, build_dir) -> str:
+    objs = []
     procs = []
     for s in SOURCES:
         obj = os.path.join(build_dir, os.path.splitext(s)[0] + ".o")
@@ -61,7 +72,9 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: 
     if failed:
         raise RuntimeError("nvcc failed")
     # the arch flag only keeps nvcc from assuming (and warning about) its default target at link time: the objects are sm_100a
-    subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path, *objs, "-cudart", "static"], check=True)
+    tmp = f"{lib_path}.tmp{os.getpid()}"  # link beside the target, then rename: a concurrent loader never sees a half-written file
+    subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs, "-cudart", "static"], check=True)
+    os.replace(tmp, lib_path)
     return lib_path
 
 
