@@ -312,10 +312,11 @@ def test_corrupted_files_never_disagree_with_the_oracle(ctx, oracle):
 
 
 @pytest.mark.parametrize("channels", [4, 6, 8])
-@pytest.mark.parametrize("bits", [1, 3, 4, 5, 8])
-def test_multichannel_pair_lane_kernel(ctx, oracle, channels, bits):
-    """decode_mc_kernel (lane per chunk and channel pair): uniform CBR batches with 4 / 6 / 8 channels, several full chunks per
-    stream plus a ragged tail (taken by the generic kernel on the side stream), quiet / loud / ordinary signals."""
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_multichannel_whole_frame_kernel(ctx, oracle, channels, bits):
+    """decode_mc_kernel (one lane per chunk with all channels, whole-frame 256-bit stores; two store phases for 6 channels):
+    uniform CBR batches with 4 / 6 / 8 channels, several full chunks per stream plus a ragged tail (taken by the generic kernel
+    on the side stream), quiet / loud / ordinary signals."""
     files, refs = [], []
     for i in range(5):
         frames = 5120 * (1 + i % 3) + (i * 997) % 5120
@@ -327,6 +328,21 @@ def test_multichannel_pair_lane_kernel(ctx, oracle, channels, bits):
         else:
             pcm = synth.gen_stream(400 + i, frames, channels, 48000)
         enc = oracle.sea_encode(pcm, 48000, channels, oracle.make_settings(float(bits)))
+        files.append(enc)
+        refs.append(oracle.sea_decode(enc).samples)
+    for o, r in zip(ctx.decode_batch(files), refs):
+        assert np.array_equal(o.samples, r)
+
+
+@pytest.mark.parametrize("channels,fpc", [(6, 5100), (6, 5080), (6, 40), (8, 1000), (8, 20), (4, 60), (4, 5100)])
+def test_multichannel_other_chunk_lengths(ctx, oracle, channels, fpc):
+    """Chunk lengths the whole-frame kernel takes (8 / 4 channels: any multiple of 20; 6 channels: multiples of 40, whose rows
+    stay 32-byte aligned) and the ones that must fall through to the generic kernel (6 channels, N % 40 == 20)."""
+    files, refs = [], []
+    for i in range(3):
+        frames = fpc * (3 + i) + (i * 13) % fpc
+        pcm = synth.gen_stream(700 + i, frames, channels, 48000)
+        enc = oracle.sea_encode(pcm, 48000, channels, oracle.make_settings(3.0, frames_per_chunk=fpc))
         files.append(enc)
         refs.append(oracle.sea_decode(enc).samples)
     for o, r in zip(ctx.decode_batch(files), refs):
