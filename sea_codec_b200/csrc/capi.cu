@@ -214,7 +214,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
     std::vector<DecStream> table(job.streams);
     const bool use_vbr = fast && decode_vbr_supported(fp);  // the VBR twin of the unrolled kernel: same split, same constraints
-    // more than two channels (CBR): lanes per (chunk, channel pair), decode_mc.cu; its left-overs go to the generic kernel
+    // more than two channels (CBR): one lane per chunk with all its channels, decode_mc.cu; its left-overs go to the generic kernel
     bool mc = !fast && fp.channels > 2 && (fp.hdr_word >> 24) == 0x5Au && decode_mc_supported(fp);
     bool unrolled = ((fast && (use_vbr || decode_unrolled_supported(fp))) || mc) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
     const uint64_t tail_slack = mc ? 512u : (use_vbr ? 320u : 128u);  // bytes the kernels may read past the last chunk they are given

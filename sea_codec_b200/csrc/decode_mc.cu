@@ -1,14 +1,12 @@
 // decode_mc.cu -- throughput decode for uniform CBR batches with MORE than two channels (4, 6 or 8; BASELINE config 3 is an
 // 8-channel stream): decode_mc_kernel<CT, B>.
 //
-// Lane mapping: one lane per (chunk, channel PAIR).  In the [frame][channel] bit stream (chunk.rs:254-278) the two codes of a
-// pair are adjacent, and the pairs of one frame follow each other, so lane (g, p) reads a stereo-like stream whose frames are
-// CT*B bits apart, starting 2*p*B bits into the residual section.  Each lane keeps two LMS chains in registers (the ILP of the
-// stereo kernel) and CT/2 neighbouring lanes cover one chunk.  Everything else is borrowed from decode_unrolled_kernel /
-// decode_vbr_kernel: per-lane cp.async ring (every lane stages the chunk's bytes it walks through), a window of big-endian
-// words per body pre-shifted once so that every field position inside the body is a compile-time constant, one shift per pair of
-// codes, I2IP pack-saturate clamp, LMS signs carried in registers.  PCM: one 32-bit store per frame and lane; the CT/2 lanes of a
-// chunk write the CT interleaved samples of a frame side by side.
+// Lane mapping: one lane per chunk with ALL its channels (MCfg::CPL == CT; the first versions gave a lane one channel pair, then
+// a quad: see MCfg).  In the [frame][channel] bit stream (chunk.rs:254-278) a frame's CT codes are adjacent, so the lane walks
+// the residual section front to back with CT independent LMS chains in registers (the ILP of the stereo kernel and more) and
+// owns whole PCM frames: they leave as full 32-byte sectors.  Everything else is borrowed from decode_unrolled_kernel /
+// decode_vbr_kernel: per-lane cp.async ring, a window of big-endian words per body pre-shifted once so that every field
+// position inside the body is a compile-time constant, I2IP pack-saturate clamp, LMS signs carried in registers.
 #include "sea_kernels.h"
 
 namespace sea {
