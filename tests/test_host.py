@@ -213,3 +213,31 @@ def test_direct_quantiser_thresholds_equal_the_closed_form():
                 theta = 2 * (q + 1) - 1 if rem else 2 * q
                 got += (A >= theta)
             assert np.array_equal(got, want), (b, rc)
+
+
+def test_register_bitonic_network_sorts():
+    """The compare-exchange schedule of warp_sort_512 (encode_kernels.cu: element e = r * 32 + lane, distance j < 32 by shuffle,
+    j >= 32 between registers, direction from (e & k)) restated on arrays: it must sort any 512 keys ascending, ties included
+    (the kernel's keys are unique: (rank << 9) | index)."""
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        n = [512, 512, 300, 256, 2, 0][trial]
+        keys = rng.integers(0, 1 << 20 if trial else 4, size=512).astype(np.uint64)
+        v = np.where(np.arange(512) < n, (keys << np.uint64(9)) | np.arange(512, dtype=np.uint64), np.uint64(0xFFFFFFFFFFFFFFFF))
+        e = np.arange(512)
+        k = 2
+        while k <= 512:
+            j = k >> 1
+            while j > 0:
+                other = v[e ^ j]
+                up = (e & k) == 0
+                lower = (e & j) == 0
+                take_min = lower == up
+                v = np.where((other < v) == take_min, other, v)
+                j >>= 1
+            k <<= 1
+        assert np.all(v[:-1] <= v[1:])
+        if n:
+            order = (v[:n] & np.uint64(511)).astype(np.int64)
+            want = np.lexsort((np.arange(n), keys[:n]))  # by (key, index): the tie rule of SURVEY trap T13
+            assert np.array_equal(order, want)
