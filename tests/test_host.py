@@ -241,3 +241,32 @@ def test_register_bitonic_network_sorts():
             order = (v[:n] & np.uint64(511)).astype(np.int64)
             want = np.lexsort((np.arange(n), keys[:n]))  # by (key, index): the tie rule of SURVEY trap T13
             assert np.array_equal(order, want)
+
+
+def test_sum32_penalty_proof_is_sufficient():
+    """encode_kernels.cu, kRankSum32: whenever max|w(0)| + (sum|d| >> 4) + 20 <= 32767 over a 20-frame block, the weights
+    penalty of lms.rs:53-62 computed with 32-bit wrapping sums and one 32-bit accumulator equals the exact value."""
+    rng = np.random.default_rng(11)
+    M32 = (1 << 32) - 1
+    proved = 0
+    for trial in range(3000):
+        scale = int(rng.choice([200, 3000, 12000, 30000]))
+        w = [int(x) for x in rng.integers(-scale, scale + 1, size=4)]
+        dmax = int(rng.choice([50, 2000, 25245]))
+        m0 = max(abs(x) for x in w)
+        dsum, exact, pen32, ok32 = 0, 0, 0, True
+        for f in range(20):
+            s = sum(x * x for x in w)
+            p = max(0, (s >> 18) - 0x8FF)
+            exact += p * p
+            s32 = sum((x * x) & M32 for x in w) & M32            # four 32-bit multiply-adds
+            t = max(0, ((s32 >> 18) - 0x8FF))                    # VIADDMNMX on the (31-bit) shifted sum
+            pen32 = (pen32 + t * t) & M32
+            d = int(rng.integers(-dmax, dmax + 1))
+            dsum += abs(d)
+            delta = d >> 4
+            w = [x + delta * int(rng.choice([-1, 1])) for x in w]
+        if m0 + (dsum >> 4) + 20 <= 32767:
+            proved += 1
+            assert pen32 == exact, (trial, m0, dsum)
+    assert proved > 300
