@@ -214,11 +214,20 @@ int sea_b200_csea_decode(uint8_t *encoded, uint32_t encoded_len, uint32_t *sampl
 /* INT32 issue-rate micro-kernel (encoder roofline denominator).  mode 0: IMAD chains (fma pipe),
  * 1: IADD3/LOP3 chains (alu pipe), 2: interleaved.  Returns lane-ops/s in *ops_per_s, kernel ms in *ms. */
 int sea_b200_int32_peak(sea_b200_ctx *ctx, int mode, double *ops_per_s, double *ms);
+/* Synthetic tone + noise PCM generated in place on the device (bench.py inputs; SURVEY 8d "Synthetic input"): stream i of the
+ * batch gets the samples sea_codec_b200/synth.py:gen_stream(stream_ids[i], ...) computes on the host, bit for bit -- interleaved
+ * i16 at d_pcm + i*stream_stride_samples.  phase_steps[i] = round(f/rate * 2^32) of the stream's tone and the 4096-entry sine
+ * table are computed by the caller in float64 (the device does integer arithmetic only). */
+int sea_b200_synth_pcm_device(sea_b200_ctx *ctx, int16_t *d_pcm, uint64_t stream_stride_samples, uint32_t n_streams, uint32_t n_frames,
+                              uint32_t channels, const uint32_t *stream_ids, const uint32_t *phase_steps,
+                              const int32_t *sine_table_4096, uint64_t seed, int32_t amplitude, int32_t noise_amplitude);
 /* Duration (ms, CUDA events on the context's stream) of the kernels launched by the last batch call. */
 double sea_b200_last_kernel_ms(const sea_b200_ctx *ctx);
 /* VBR blocks whose error tied across a bucket boundary in the last encode (sort_unstable order is unspecified in the
  * reference, encoder_vbr.rs:102-103; this library orders by (error, index)).  0 means bit-exactness is well defined. */
 uint64_t sea_b200_last_vbr_ties(const sea_b200_ctx *ctx);
+/* The same count per stream of the last batch encode: ties[i] for i < n_streams (bench.py selects tie-free inputs with it). */
+int sea_b200_last_vbr_ties_per_stream(const sea_b200_ctx *ctx, uint64_t *ties, uint32_t n_streams);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,42 @@
  * clearing the cache key (c/sea.h:52-55, :225), so a second call in the same process would read freed
  * memory.  The wrapper resets those statics after every full decode; parallel timing uses fork().
  */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/*
+ * LMS capture (tests only).  sea_read_chunk keeps its per-channel LMS in a malloc'ed block that it frees at the end of the
+ * chunk (c/sea.h:147-185), so the state the REFERENCE decoder reached at each chunk end is never visible to a caller.  The
+ * two macros below route c/sea.h's own malloc/free calls through this file; its source is still compiled where it lies,
+ * unmodified.  sea_read_chunk frees exactly three blocks per chunk, in the order residuals, scale_factors, lms
+ * (c/sea.h:181-183); the only other free is the dequant table (pointer == SEA_DQT).  The third one is copied out.
+ */
+static void *ref_hook_malloc(size_t n);
+static void ref_hook_free(void *p);
+#define malloc(n) ref_hook_malloc(n)
+#define free(p) ref_hook_free(p)
 #include "sea.h"
+#undef malloc
+#undef free
+
+static int32_t *g_cap = NULL;      /* [chunk][channel][8]: history[4], weights[4] as c/sea.h holds them (int32) */
+static uint32_t g_cap_chunks = 0;  /* capacity in chunks */
+static uint32_t g_cap_channels = 0, g_cap_n = 0, g_free_no = 0;
+
+static void *ref_hook_malloc(size_t n) { return malloc(n); }
+static void ref_hook_free(void *p)
+{
+    if (p != (void *)SEA_DQT && g_cap) {
+        if (++g_free_no % 3u == 0u && g_cap_n < g_cap_chunks) {
+            memcpy(g_cap + (size_t)g_cap_n * g_cap_channels * 8u, p, (size_t)g_cap_channels * sizeof(SEA_LMS));
+            g_cap_n++;
+        }
+    }
+    free(p);
+}
 
 #include <sys/wait.h>
 #include <time.h>
@@ -25,6 +60,23 @@ int ref_csea_decode(uint8_t *encoded, uint32_t encoded_len, uint32_t *sample_rat
         SEA_DQT_SCALE_FACTOR_BITS = 0;
         SEA_DQT_RESIDUAL_BITS = 0;
     }
+    return rc;
+}
+
+/* Full decode that also returns, for every chunk, the LMS state c/sea.h held when the chunk ended: lms_out[chunk][channel][8]
+ * (history[4] then weights[4], int32).  *n_chunks receives how many were captured (<= max_chunks). */
+int ref_csea_decode_capture_lms(uint8_t *encoded, uint32_t encoded_len, uint32_t *sample_rate, uint32_t *channels, int16_t *output,
+                                uint32_t *total_frames, int32_t *lms_out, uint32_t max_chunks, uint32_t *n_chunks)
+{
+    if (encoded_len < 22 || !output || !lms_out) return 1;
+    g_cap = lms_out;
+    g_cap_chunks = max_chunks;
+    g_cap_channels = encoded[5];
+    g_cap_n = 0;
+    g_free_no = 0;
+    int rc = ref_csea_decode(encoded, encoded_len, sample_rate, channels, output, total_frames);
+    g_cap = NULL;
+    if (n_chunks) *n_chunks = g_cap_n;
     return rc;
 }
 

@@ -100,6 +100,9 @@ def ref():
         R.ref_csea_decode.restype = C.c_int
         R.ref_csea_decode.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p,
                                       C.POINTER(C.c_uint32)]
+        R.ref_csea_decode_capture_lms.restype = C.c_int
+        R.ref_csea_decode_capture_lms.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p,
+                                                  C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         _ref = R
     return _ref
 
@@ -166,6 +169,41 @@ def ref_c_decode(encoded: bytes) -> DecodeInfo:
     if rc:
         raise OracleError(rc, "ref c/sea.h decode")
     return DecodeInfo(out[: frames.value * ch.value].copy(), rate.value, ch.value)
+
+
+def ref_c_decode_lms(encoded: bytes):
+    """c/sea.h decode that also returns the LMS state the REFERENCE decoder held at the end of every chunk
+    (oracle/ref_csea.c capture hook): (DecodeInfo, lms[chunk][channel][8] int32 = history[4] then weights[4])."""
+    R = ref()
+    buf = np.frombuffer(encoded, dtype=np.uint8).copy()
+    rate, ch, frames = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    rc = R.ref_csea_decode(buf.ctypes.data, buf.size, C.byref(rate), C.byref(ch), None, C.byref(frames))
+    if rc:
+        raise OracleError(rc, "ref c/sea.h header")
+    fpc = encoded[8] | (encoded[9] << 8)
+    n_chunks = (frames.value + fpc - 1) // fpc
+    out = np.zeros(frames.value * ch.value + fpc * ch.value + 4096, dtype=np.int16)
+    lms = np.zeros((max(n_chunks, 1), ch.value, 8), dtype=np.int32)
+    got = C.c_uint32(0)
+    rc = R.ref_csea_decode_capture_lms(buf.ctypes.data, buf.size, C.byref(rate), C.byref(ch), out.ctypes.data, C.byref(frames),
+                                       lms.ctypes.data, n_chunks, C.byref(got))
+    if rc:
+        raise OracleError(rc, "ref c/sea.h decode")
+    assert got.value == n_chunks, (got.value, n_chunks)
+    return DecodeInfo(out[: frames.value * ch.value].copy(), rate.value, ch.value), lms[:n_chunks]
+
+
+def chunk_header_lms(encoded: bytes) -> np.ndarray:
+    """The LMS block of every chunk header as written (lms.rs:64-78: 4 x i16 history, 4 x i16 weights per channel, LE):
+    int16 array [chunk][channel][8].  Full chunks sit chunk_size apart from byte 22 (file.rs:185)."""
+    ch = encoded[5]
+    cs = encoded[6] | (encoded[7] << 8)
+    n = (len(encoded) - 22 + cs - 1) // cs
+    out = np.zeros((n, ch, 8), dtype=np.int16)
+    for k in range(n):
+        base = 22 + k * cs + 4
+        out[k] = np.frombuffer(encoded, dtype="<i2", count=ch * 8, offset=base).reshape(ch, 8)
+    return out
 
 
 class StreamingEncoder:

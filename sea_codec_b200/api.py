@@ -145,6 +145,9 @@ SYMBOLS = {
     "sea_b200_int32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sea_b200_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "sea_b200_last_vbr_ties": (C.c_uint64, [C.c_void_p]),
+    "sea_b200_last_vbr_ties_per_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sea_b200_synth_pcm_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]),
 }
 
 _lib = None
@@ -219,6 +222,22 @@ class Context:
     @property
     def last_vbr_ties(self) -> int:
         return self._L.sea_b200_last_vbr_ties(self._h)
+
+    def last_vbr_ties_per_stream(self, n_streams: int) -> np.ndarray:
+        out = np.zeros(n_streams, dtype=np.uint64)
+        self._check(self._L.sea_b200_last_vbr_ties_per_stream(self._h, out.ctypes.data, n_streams))
+        return out
+
+    def synth_pcm_device(self, d_pcm: int, stream_stride_samples: int, stream_ids, n_frames: int, channels: int, rate: int) -> None:
+        """Fills device memory with the synthetic streams synth.gen_stream(id, n_frames, channels, rate) of the given ids."""
+        from . import synth
+
+        ids = np.ascontiguousarray(stream_ids, dtype=np.uint32)
+        steps = np.array([synth._step(int(k), rate) for k in ids], dtype=np.uint32)
+        tab = np.ascontiguousarray(synth.sine_table(), dtype=np.int32)
+        self._check(self._L.sea_b200_synth_pcm_device(self._h, C.c_void_p(d_pcm), stream_stride_samples, ids.size, n_frames, channels,
+                                                      ids.ctypes.data, steps.ctypes.data, tab.ctypes.data, synth.SEED, synth._A,
+                                                      synth._NOISE_AMP))
 
     def int32_peak(self, mode: int):
         ops, ms = C.c_double(0), C.c_double(0)

@@ -52,7 +52,8 @@ struct sea_b200_ctx {
     DevTables tabs = {};
     DevBuf in, out, streams, lens, chunk0, scratch, misc;
     int *d_err = nullptr;
-    unsigned long long *d_ties = nullptr;
+    DevBuf ties;  // [0] VBR boundary ties of the last encode, [1 + i] those of its stream i
+    std::vector<unsigned long long> h_ties;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side = nullptr;                       // partial-chunk decode runs beside the full-chunk kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -217,15 +218,32 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     // more than two channels (CBR): one lane per chunk with all its channels, decode_mc.cu; its left-overs go to the generic kernel
     bool mc = !fast && fp.channels > 2 && (fp.hdr_word >> 24) == 0x5Au && decode_mc_supported(fp);
     bool unrolled = ((fast && (use_vbr || decode_unrolled_supported(fp))) || mc) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
-    const uint64_t tail_slack = mc ? 512u : (use_vbr ? 320u : 128u);  // bytes the kernels may read past the last chunk they are given
+    // The lane-per-chunk kernels do not look at data_len: every lane walks the layout its chunk header implies.  They therefore
+    // only get chunks that are completely present, in streams whose header.chunk_size holds that layout (a crafted small
+    // chunk_size -- file.rs:33-38 accepts >= 16 -- would otherwise let a lane read far past its chunk), and `extent` = the most
+    // a lane can read from its chunk's first byte must lie inside the buffer.  Everything else goes to the staged / generic
+    // kernels, which check every section against the bytes available (chunk.rs:81-196 slice bounds).
+    uint64_t extent = 0;
+    if (unrolled) {
+        const uint64_t items = (uint64_t)(fp.N / fp.F) * fp.channels;
+        const uint64_t res_rel = 4u + 16u * fp.channels + (items * fp.s + 7u) / 8u + (use_vbr ? (items * 2u + 7u) / 8u : 0u);
+        if (use_vbr) {
+            extent = res_rel + (uint64_t)fp.N * fp.channels + 320u;  // sizes are clamped to <= 8 bits per sample inside the kernel
+            if (fp.chunk_size < res_rel) unrolled = false;
+        } else {
+            const uint64_t layout = res_rel + ((uint64_t)fp.N * fp.channels * fp.b + 7u) / 8u;
+            extent = layout + (mc ? 512u : 128u);
+            if (fp.chunk_size < layout) unrolled = false;
+        }
+    }
     uint64_t chains_a = 0, chains_b = 0;
     if (unrolled) {
         table.resize((size_t)3 * n_streams);
         for (uint32_t i = 0; i < n_streams && unrolled; i++) {
             const DecStream &d = job.streams[i];
             if (d.pcm_off % 16) unrolled = false;  // 256-bit stores need 32-byte aligned rows
-            uint64_t n_full = std::min<uint64_t>(d.total_frames / fp.N, d.n_chunks);
-            while (n_full > 0 && d.data_off + n_full * fp.chunk_size + tail_slack > sea_len) n_full--;
+            uint64_t n_full = std::min<uint64_t>(std::min<uint64_t>(d.total_frames / fp.N, d.n_chunks), d.data_len / fp.chunk_size);
+            while (n_full > 0 && d.data_off + (n_full - 1u) * fp.chunk_size + extent > sea_len) n_full--;
             DecStream a = d, b = d;
             a.n_chunks = (uint32_t)n_full;
             a.total_frames = (uint32_t)(n_full * fp.N);
@@ -370,22 +388,42 @@ int run_encode(sea_b200_ctx *ctx, EncodeJob &job, const int16_t *d_pcm, uint8_t 
     }
     CU(cudaMemcpyAsync(ctx->streams.p, job.streams.data(), sizeof(EncStream) * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_ties, 0, sizeof(unsigned long long), ctx->stream));
+    CU(ctx->ties.reserve(sizeof(unsigned long long) * ((size_t)n + 1u)));
+    CU(cudaMemsetAsync(ctx->ties.p, 0, sizeof(unsigned long long) * ((size_t)n + 1u), ctx->stream));
+    ctx->h_ties.assign((size_t)n + 1u, 0ull);
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CU(launch_encode_generic(d_pcm, d_out, ctx->streams.as<EncStream>(), job.params, ctx->tabs, d_state, ctx->lens.as<uint64_t>(),
-                             ctx->chunk0.as<uint32_t>(), ctx->d_ties, ws, ctx->d_err, ctx->stream));
+                             ctx->chunk0.as<uint32_t>(), ctx->ties.as<unsigned long long>(), ws, ctx->d_err, ctx->stream));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     int dev_err = 0;
     CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->last_ties, ctx->d_ties, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (job.params.vbr)
+        CU(cudaMemcpyAsync(ctx->h_ties.data(), ctx->ties.p, sizeof(unsigned long long) * ((size_t)n + 1u), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(h_out_lens, ctx->lens.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_chunk0) CU(cudaMemcpyAsync(h_chunk0, ctx->chunk0.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;
+    ctx->last_ties = ctx->h_ties[0];
     return map_dev_error(ctx, dev_err);
+}
+
+// Half-open ranges of a caller buffer that a batch call owns; sorted and coalesced so that one copy serves each run of
+// adjacent streams and nothing outside an owned range is ever written.
+struct Run {
+    uint64_t lo, hi;
+};
+void merge_runs(std::vector<Run> &runs)
+{
+    std::sort(runs.begin(), runs.end(), [](const Run &a, const Run &b) { return a.lo < b.lo; });
+    size_t n = 0;
+    for (const Run &r : runs) {
+        if (n && r.lo <= runs[n - 1].hi) runs[n - 1].hi = std::max(runs[n - 1].hi, r.hi);
+        else runs[n++] = r;
+    }
+    runs.resize(n);
 }
 
 uint64_t encode_bound_bytes(const EncodePlan &pl, uint64_t n_frames)
@@ -466,7 +504,6 @@ int sea_b200_ctx_create(int device, sea_b200_ctx **out)
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&ctx->d_ties, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     for (uint32_t s = 1; s <= 8; s++) {  // SeaDequantTab::init for every scale_factor_bits a chunk header can name
         std::vector<int32_t> t = build_tables(s);
         if ((e = cudaMalloc(&ctx->d_tab[s], t.size() * sizeof(int32_t))) != cudaSuccess) return bail(e);
@@ -493,7 +530,7 @@ void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
     ctx->scratch.release();
     ctx->misc.release();
     if (ctx->d_err) cudaFree(ctx->d_err);
-    if (ctx->d_ties) cudaFree(ctx->d_ties);
+    ctx->ties.release();
     if (ctx->aux.stream) { cudaStreamSynchronize(ctx->aux.stream); cudaStreamDestroy(ctx->aux.stream); }
     if (ctx->aux.side) { cudaStreamSynchronize(ctx->aux.side); cudaStreamDestroy(ctx->aux.side); }
     if (ctx->aux.ev_fork) cudaEventDestroy(ctx->aux.ev_fork);
@@ -530,6 +567,12 @@ const char *sea_b200_last_error(const sea_b200_ctx *ctx) { return ctx ? ctx->las
 uint64_t sea_b200_ctx_launch_count(const sea_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 double sea_b200_last_kernel_ms(const sea_b200_ctx *ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 uint64_t sea_b200_last_vbr_ties(const sea_b200_ctx *ctx) { return ctx ? ctx->last_ties : 0; }
+int sea_b200_last_vbr_ties_per_stream(const sea_b200_ctx *ctx, uint64_t *ties, uint32_t n_streams)
+{
+    if (!ctx || !ties) return SEA_B200_ERR_INVALID_PARAMETERS;
+    for (uint32_t i = 0; i < n_streams; i++) ties[i] = (size_t)i + 1u < ctx->h_ties.size() ? ctx->h_ties[(size_t)i + 1u] : 0u;
+    return SEA_B200_OK;
+}
 
 void *sea_b200_host_alloc(size_t bytes)
 {
@@ -716,6 +759,7 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         return cudaMemcpyAsync(L.in->p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, L.stream);
     };
     double kernel_ms = 0.0;
+    std::vector<Run> runs;
     CU(upload(0));
     for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
         const Group &q = groups[gi];
@@ -747,8 +791,16 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         }
         rc = run_decode(ctx, L, sub, L.in->as<uint8_t>(), q.hi - q.lo, L.out->as<int16_t>(), have, hdr_word);
         kernel_ms += L.kernel_ms;
-        if (rc == SEA_B200_OK && q.phi > q.plo)
-            CU(cudaMemcpyAsync(pcm + q.plo, L.out->p, (q.phi - q.plo) * 2, cudaMemcpyDeviceToHost, L.stream));
+        if (rc == SEA_B200_OK && q.phi > q.plo) {
+            // only the ranges the streams own go back: whatever lies between them in the caller's buffer is not ours to touch
+            // (one copy per run of adjacent streams; a packed layout is a single run)
+            runs.clear();
+            for (uint32_t i = q.i0; i < q.i1; i++)
+                if (job.n_samples[i]) runs.push_back({pcm_offsets[i], pcm_offsets[i] + job.n_samples[i]});
+            merge_runs(runs);
+            for (const Run &r : runs)
+                CU(cudaMemcpyAsync(pcm + r.lo, L.out->as<int16_t>() + (r.lo - q.plo), (r.hi - r.lo) * 2, cudaMemcpyDeviceToHost, L.stream));
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));
     if (piped) CU(cudaStreamSynchronize(ctx->aux.stream));
@@ -826,13 +878,13 @@ int sea_b200_encode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const int16_t *
     if (hi) CU(cudaMemcpyAsync(ctx->in.p, pcm + lo, (hi - lo) * 2, cudaMemcpyHostToDevice, ctx->stream));
     rc = run_encode(ctx, job, ctx->in.as<int16_t>(), ctx->out.as<uint8_t>(), nullptr, out_lens, nullptr);
     if (rc) return rc;
-    // ship back only what was written
-    uint64_t wlo = UINT64_MAX, whi = 0;
-    for (uint32_t i = 0; i < n_streams; i++) {
-        wlo = std::min(wlo, out_offsets[i]);
-        whi = std::max(whi, out_offsets[i] + out_lens[i]);
-    }
-    CU(cudaMemcpyAsync(out + wlo, ctx->out.as<uint8_t>() + (wlo - olo), whi - wlo, cudaMemcpyDeviceToHost, ctx->stream));
+    // ship back only what was written, and only into the ranges the streams own (one copy per run of adjacent streams)
+    std::vector<Run> runs;
+    for (uint32_t i = 0; i < n_streams; i++)
+        if (out_lens[i]) runs.push_back({out_offsets[i], out_offsets[i] + out_lens[i]});
+    merge_runs(runs);
+    for (const Run &r : runs)
+        CU(cudaMemcpyAsync(out + r.lo, ctx->out.as<uint8_t>() + (r.lo - olo), r.hi - r.lo, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SEA_B200_OK;
 }
@@ -913,6 +965,10 @@ int sea_b200_encoder_make_chunks(sea_b200_encoder *enc, const int16_t *pcm, uint
     EncodeJob job;
     int rc = plan_encode(ctx, 1, &zero, &frames, enc->sample_rate, enc->channels, &enc->settings, &zero, true, &job);
     if (rc) return rc;
+    // The kernel advances the handle's LMS / prev_scalefactor state, so a too-small buffer must be refused BEFORE the launch
+    // (a caller retrying with a larger one would otherwise encode the same PCM from already-advanced state).
+    if (out_cap < encode_bound_bytes(pl, frames) - kFileHeaderBytes)
+        return fail(ctx, SEA_B200_ERR_CAPACITY, "chunk buffer smaller than the bound for these frames (sea_b200_encode_bound - 22)");
     CU(ctx->in.reserve(n_samples * 2 + 64));
     CU(ctx->out.reserve((uint64_t)chunks * pl.max_chunk_bytes + 64));
     CU(cudaMemcpyAsync(ctx->in.p, pcm, n_samples * 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -920,7 +976,7 @@ int sea_b200_encoder_make_chunks(sea_b200_encoder *enc, const int16_t *pcm, uint
     uint32_t first = 0;
     rc = run_encode(ctx, job, ctx->in.as<int16_t>(), ctx->out.as<uint8_t>(), enc->d_state, &len, &first);
     if (rc) return rc;
-    if (len > out_cap) return fail(ctx, SEA_B200_ERR_CAPACITY, "chunk buffer too small");
+    if (len > out_cap) return fail(ctx, SEA_B200_ERR_CAPACITY, "chunk buffer too small");  // unreachable: len <= the bound above
     CU(cudaMemcpyAsync(out, ctx->out.p, len, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (enc->chunk_size == 0) enc->chunk_size = first & 0xffffu;  // file.rs:166-168 (`as u16`)
@@ -963,6 +1019,19 @@ int sea_b200_decoder_header(const sea_b200_decoder *dec, sea_b200_header *out)
 
 void sea_b200_decoder_destroy(sea_b200_decoder *dec) { delete dec; }
 
+// Decoder::init + the scale_factor_bits assert of codec/decoder.rs:21 for a run of chunks (`stride` bytes apart): the first
+// chunk a handle sees fixes scale_factor_bits, every later one must agree.  Shared by decode_chunk and decode_chunks.
+__attribute__((visibility("hidden"))) int sea_b200_internal_check_sf_bits(sea_b200_decoder *dec, const uint8_t *chunks, uint64_t len,
+                                                                         uint64_t stride)
+{
+    for (uint64_t off = 0; off + 2 <= len; off += stride) {
+        const int sfb = chunks[off + 1] >> 4;
+        if (dec->sf_bits < 0) dec->sf_bits = sfb;
+        else if (dec->sf_bits != sfb) return fail(dec->ctx, SEA_B200_ERR_DOMAIN, "scale_factor_bits changed between chunks (decoder.rs:21 assert)");
+    }
+    return SEA_B200_OK;
+}
+
 int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, uint64_t len, int64_t remaining_frames, int16_t *pcm,
                                   uint64_t pcm_cap_samples, uint64_t *n_samples)
 {
@@ -975,9 +1044,7 @@ int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, u
     if (remaining_frames < 0 && len < h.chunk_size) return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "short chunk in streaming mode (chunk.rs:76-79)");
     if (len < 4) return fail(ctx, SEA_B200_ERR_DOMAIN, "chunk shorter than its header");
     if (chunk[0] != 1 && chunk[0] != 2) return fail(ctx, SEA_B200_ERR_INVALID_FRAME, "chunk type is neither CBR nor VBR (chunk.rs:81-85)");
-    const int sfb = chunk[1] >> 4;
-    if (dec->sf_bits < 0) dec->sf_bits = sfb;
-    else if (dec->sf_bits != sfb) return fail(ctx, SEA_B200_ERR_DOMAIN, "scale_factor_bits changed between chunks (decoder.rs:21 assert)");
+    if (int rcs = sea_b200_internal_check_sf_bits(dec, chunk, len, h.chunk_size)) return rcs;
     uint64_t frames = h.frames_per_chunk;
     if (remaining_frames >= 0 && (uint64_t)remaining_frames < frames) frames = (uint64_t)remaining_frames;
     if (frames == 0) return SEA_B200_OK;
@@ -1013,6 +1080,29 @@ int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, u
 }
 
 // ------------------------------------------------------------------------------------------------ measurement
+
+int sea_b200_synth_pcm_device(sea_b200_ctx *ctx, int16_t *d_pcm, uint64_t stream_stride_samples, uint32_t n_streams, uint32_t n_frames,
+                              uint32_t channels, const uint32_t *stream_ids, const uint32_t *phase_steps, const int32_t *sine_table_4096,
+                              uint64_t seed, int32_t amplitude, int32_t noise_amplitude)
+{
+    if (!ctx || !d_pcm || !stream_ids || !phase_steps || !sine_table_4096 || channels == 0 || noise_amplitude < 0)
+        return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (n_streams == 0 || n_frames == 0) return SEA_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t idb = sizeof(uint32_t) * (size_t)n_streams;
+    CU(ctx->misc.reserve(2 * idb + 4096 * sizeof(int32_t) + 256));
+    uint8_t *base = ctx->misc.as<uint8_t>();
+    const size_t tab_off = (2 * idb + 255) & ~(size_t)255;
+    CU(cudaMemcpyAsync(base, stream_ids, idb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + idb, phase_steps, idb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + tab_off, sine_table_4096, 4096 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_synth(d_pcm, stream_stride_samples, n_streams, n_frames, channels, reinterpret_cast<const uint32_t *>(base),
+                    reinterpret_cast<const uint32_t *>(base + idb), reinterpret_cast<const int32_t *>(base + tab_off), seed, amplitude,
+                    noise_amplitude, ctx->stream));
+    ctx->launches += (n_streams + 65534u) / 65535u;
+    CU(cudaStreamSynchronize(ctx->stream));  // the id / step / table arrays are the caller's: done with them on return
+    return SEA_B200_OK;
+}
 
 int sea_b200_int32_peak(sea_b200_ctx *ctx, int mode, double *ops_per_s, double *ms_out)
 {

@@ -11,6 +11,9 @@
 
 #include "../../include/sea_b200.h"
 
+// capi.cu (not part of the public header): the decoder.rs:21 scale_factor_bits consistency check over a run of chunks
+extern "C" __attribute__((visibility("hidden"))) int sea_b200_internal_check_sf_bits(sea_b200_decoder *dec, const uint8_t *chunks, uint64_t len, uint64_t stride);
+
 namespace {
 
 void put_le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
@@ -114,6 +117,7 @@ int sea_b200_decoder_decode_chunks(sea_b200_decoder *dec, sea_b200_ctx *ctx, con
     if (frames == 0) return SEA_B200_OK;
     if (frames > 0xffffffffull) return SEA_B200_ERR_TOO_MANY_FRAMES;
     if (frames * h.channels > pcm_cap_samples) return SEA_B200_ERR_CAPACITY;
+    if ((rc = sea_b200_internal_check_sf_bits(dec, chunks, len, h.chunk_size)) != SEA_B200_OK) return rc;
     std::vector<uint8_t> file(SEA_B200_FILE_HEADER_BYTES + len);
     write_header(file.data(), h, (uint32_t)frames);
     memcpy(file.data() + SEA_B200_FILE_HEADER_BYTES, chunks, len);

@@ -11,6 +11,8 @@
 // SURVEY trap T4), a shuffle arg-min on the key (rank, (sf - prev_sf) mod 2^s) picks what the sequential
 // reference loop would have kept (trap T1), and the winner's state is written back before the next block.
 // The serialized chunk is assembled in shared memory as a big-endian bit string and written out per chunk.
+#include <stdlib.h>
+
 #include "sea_kernels.h"
 
 namespace sea {
@@ -189,6 +191,7 @@ __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p,
                     prefix = c * size;
                 }
                 const uint8_t *wbuf = codes + (size_t)g_buf * F * T + (threadIdx.x - lane + g_lane);
+                __syncwarp(__activemask());  // the winner's codes were written by another lane (shuffles do not order memory)
                 for (uint32_t f = lic; f < nf; f += lpc)
                     put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[(size_t)f * T]);
             }
@@ -271,15 +274,21 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
     const uint32_t C = p.channels, F = p.F;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t grp = lane >> 4, sf = lane & 15u;
-    const uint32_t slots = nwarps * cpw;
+    // p.split (few streams, launch_encode_generic): ONE channel per warp -- BASELINE's "one warp per (stream, channel)".  A warp's
+    // step costs the same issue slots whether 16 or 32 of its lanes carry a chain, and with fewer warps than sub-partitions
+    // every warp runs alone at its own latency, so halving the chains per warp halves the time.  Both lane groups then run the
+    // same chain (identical registers, identical votes); group 0 owns the side effects.
+    const bool split = p.split != 0u;
+    const uint32_t cstep = split ? 1u : cpw;
+    const uint32_t slots = nwarps * cstep;
     const uint32_t T = blockDim.x;
     const uint32_t nblk = div_ceil_u32(frames, F);
     int16_t *xbuf = xbuf_all + warp * (cpw * F);  // [chain group][frame]
 
-    for (uint32_t cb = warp * cpw; cb < C; cb += slots) {  // warp-uniform: this warp's pair of channels
-        const uint32_t c_raw = cb + grp;
-        const bool active = c_raw < C;
-        const uint32_t c = active ? c_raw : C - 1u;
+    for (uint32_t cb = warp * cstep; cb < C; cb += slots) {  // warp-uniform: this warp's pair of channels (split: its channel)
+        const uint32_t c_raw = split ? cb : cb + grp;
+        const bool active = c_raw < C && !(split && grp != 0u);
+        const uint32_t c = c_raw < C ? c_raw : C - 1u;
         // stage block 0: lane l < F brings frame l of both chains
         {
             const uint32_t nf0 = frames < F ? frames : F;
@@ -371,7 +380,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             }
             const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
             unsigned long long rank = 0;
-            const int16_t *xs = xbuf + grp * F;
+            const int16_t *xs = xbuf + (split ? 0u : grp * F);
             uint8_t *cbuf = codes + warp * (F * 32u) + lane;  // [frame][lane] per warp: constant stride, immediate offsets when unrolled
             // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
             bool direct_now = kDirect;
@@ -720,7 +729,7 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
     int32_t *sv_w = st_prev + C;
     int32_t *sv_h = sv_w + 4 * C;
     uint8_t *codes = reinterpret_cast<uint8_t *>(sv_h + 4 * C);
-    __shared__ uint32_t sh_res_bits;
+    __shared__ uint32_t sh_res_bits, sh_sorted;
     // fast pass extras: per-warp sample staging and the dequant tables [size][code][sf]
     FastLut fl = {};
     int16_t *xbuf = nullptr;
@@ -849,7 +858,13 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
             }
             for (uint32_t i = tid; i < items; i += T) vs.sizes[i] = (uint8_t)p.base;
             __syncthreads();
-            if (!(T == 32u && np2 <= 512u && warp_sort_512(vs.keys, vs.idx, sortable, np2))) bitonic_sort(vs.keys, vs.idx, np2);
+            // register sort by the first warp when the items fit (<= 512: stereo chunks), else / on overflow the CTA-wide one
+            if (tid < 32u) {
+                const bool ok = np2 <= 512u && warp_sort_512(vs.keys, vs.idx, sortable, np2);
+                if (tid == 0) sh_sorted = ok ? 1u : 0u;
+            }
+            __syncthreads();
+            if (!sh_sorted) bitonic_sort(vs.keys, vs.idx, np2);
             for (uint32_t pos = tid; pos < sortable; pos += T) {
                 uint32_t size = p.base;
                 if (pos < m1) size = p.base - 1u;
@@ -863,11 +878,14 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
                     if (pos - 1 < m1) before = p.base - 1u;
                     if (pos - 1 >= sortable - p2 - p1) before = p.base + 1u;
                     if (pos - 1 >= sortable - p2) before = p.base + 2u;
-                    if (before != size) atomicAdd(ties, 1ull);  // trap T13: tie across a bucket boundary
+                    if (before != size) {  // trap T13: tie across a bucket boundary (ties[0] = batch total, ties[1 + i] = stream i)
+                        atomicAdd(ties, 1ull);
+                        atomicAdd(ties + 1u + sidx, 1ull);
+                    }
                 }
             }
             __syncthreads();
-            if (T == 32u) {  // bit offset of every block inside the residual section: a run of blocks per lane, then a warp scan
+            if (tid < 32u) {  // bit offset of every block inside the residual section: a run of blocks per lane, then a warp scan
                 const uint32_t per = (nblk + 31u) / 32u, b0 = tid * per, b1 = b0 + per < nblk ? b0 + per : nblk;
                 uint32_t mine = 0;
                 for (uint32_t blk = b0; blk < b1; blk++) {
@@ -892,18 +910,6 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
                     acc += nf * vs.rowbits[blk];
                 }
                 if (tid == 31u) sh_res_bits = incl;
-            } else if (tid == 0) {
-                uint32_t acc = 0;
-                for (uint32_t blk = 0; blk < nblk; blk++) {
-                    uint32_t rb = 0;
-                    for (uint32_t c = 0; c < C; c++) rb += vs.sizes[blk * C + c];
-                    uint32_t nf = frames - blk * F;
-                    if (nf > F) nf = F;
-                    vs.blkbit[blk] = acc;
-                    vs.rowbits[blk] = rb;
-                    acc += nf * rb;
-                }
-                sh_res_bits = acc;
             }
             for (uint32_t i = tid; i < items; i += T) {  // chunk.rs:245-252 (release build masks to 2 bits)
                 const uint32_t sz = vs.sizes[i], blk_i = i / C, c_i = i - blk_i * C;
@@ -984,12 +990,20 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
 {
     if (p.n_streams == 0) return cudaSuccess;
     const uint32_t nsf = 1u << p.s, lpc = nsf < 32u ? nsf : 32u, cpw = 32u / lpc;
-    uint32_t warps = (p.channels + cpw - 1u) / cpw;
+    // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
+    const bool fast = p.s == 4u && p.F <= 32u && p.channels <= 16u;
+    // Few streams (BASELINE config 5 sharded over 8 GPUs: 128 per GPU): a warp per channel instead of per channel pair, while
+    // that still leaves every warp a sub-partition of its own (see search_pass_fast)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    bool split = fast && p.channels >= 2u && (uint64_t)p.n_streams * p.channels <= 4ull * (uint64_t)sms;
+    if (const char *env = getenv("SEA_B200_ENC_SPLIT"))  // tests and tuning runs pin the mapping: 0 = channel pairs, 1 = one channel per warp
+        split = fast && p.channels >= 2u && env[0] == '1';
+    uint32_t warps = split ? p.channels : (p.channels + cpw - 1u) / cpw;
     if (warps > 8u) warps = 8u;
     const uint32_t T = warps * 32u;
     size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + ((2u * (size_t)p.F * T + 15u) & ~(size_t)15u) + 16u;
-    // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
-    const bool fast = p.s == 4u && p.F <= 32u && p.channels <= 16u;
     int lut_mode = kEncLut32;
     if (fast) {
         smem += ((size_t)warps * 2u * p.F * 2u + 15u) & ~(size_t)15u;
@@ -1012,6 +1026,7 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     EncParams pp = p;
     pp.vbr_smem_off = 0;
     pp.lut_mode = (uint32_t)lut_mode;
+    pp.split = split ? 1u : 0u;
     if (p.vbr) {  // keep the per-chunk VBR scratch in shared memory when it is small (stereo: 8.7 KB)
         const uint64_t sc = enc_vbr_scratch_bytes(p);
         if (sc <= 40u * 1024u && smem + sc + 16u <= 200u * 1024u) {

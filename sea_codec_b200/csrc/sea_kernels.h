@@ -80,6 +80,7 @@ struct EncParams {
     uint32_t n_streams;
     uint32_t vbr_smem_off;     // != 0: the VBR scratch (ranks, sort keys, sizes) lives in shared memory at this offset
     uint32_t lut_mode;         // VBR fast pass: where the dequant rows live (encode_kernels.cu kEncLut*); set by the launcher
+    uint32_t split;            // fast pass: 1 = one warp per channel (few streams), 0 = one warp per channel pair; set by the launcher
 };
 
 // Persistent per-channel encoder state (EncoderBase.lms + prev_scalefactor, encoder_base.rs:15-19): 9 int32 per channel
@@ -100,5 +101,8 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
 
 // ---- measurement -------------------------------------------------------------------------------------------
 cudaError_t launch_int32_peak(int mode, uint32_t *d_sink, uint64_t *lane_ops, cudaStream_t stream);
+// synthetic tone + noise PCM of sea_codec_b200/synth.py, generated in place on the device (bench inputs)
+cudaError_t launch_synth(int16_t *d_pcm, uint64_t stream_stride, uint32_t n_streams, uint32_t n_frames, uint32_t channels, const uint32_t *d_ids,
+                         const uint32_t *d_steps, const int32_t *d_sine, uint64_t seed, int32_t amp, int32_t noise_amp, cudaStream_t stream);
 
 }  // namespace sea

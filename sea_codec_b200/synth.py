@@ -15,6 +15,7 @@ _TAB_BITS = 12
 _A = 16383  # 0.5 * 32767
 _NOISE_AMP = 1638  # 0.05 * 32767
 _MASK64 = (1 << 64) - 1
+SEED = 0x5EA0000
 
 
 def sine_table() -> np.ndarray:

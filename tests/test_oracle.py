@@ -130,6 +130,30 @@ def test_oracle_matches_reference_c_decoder(oracle, channels, bits, sfb):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("channels,bits,sfb", [(1, 1, 4), (1, 3, 4), (2, 3, 4), (2, 5, 3), (2, 8, 5), (3, 4, 4), (8, 4, 4), (2, 2, 4), (2, 6, 4),
+                                               (1, 7, 4)])
+def test_reference_decoder_end_state_equals_next_chunk_header(oracle, channels, bits, sfb):
+    """Pins the ENCODER's reconstruct/update path with reference code and no restatement in between: c/sea.h decodes the
+    encoder's output, and the LMS state it holds when chunk k ends (captured before its free, c/sea.h:147-185, by
+    oracle/ref_csea.c) must equal -- mod 2^16, lms.rs:64-78 -- the LMS block the encoder wrote into chunk k+1's header
+    (file.rs:146-149).  The last four PCM samples c/sea.h emits per channel are chunk k+1's header history as well.
+    Here for the oracle's encoder; tests/test_gpu_round2.py does the same for the GPU encoder."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    frames = 5120 * 4 + 1000
+    pcm = gen_test_signal(channels, frames, seed=channels * 10 + bits)
+    enc = oracle.sea_encode(pcm, 44100, channels, oracle.make_settings(float(bits), False, sfb))
+    info, lms = oracle.ref_c_decode_lms(enc)
+    hdr = oracle.chunk_header_lms(enc)
+    assert lms.shape == hdr.shape == (5, channels, 8)
+    assert np.array_equal(lms[:-1].astype(np.int16), hdr[1:])
+    pcm_out = info.samples.reshape(-1, channels)
+    for k in range(1, 5):  # black-box: history of chunk k's header = the reference decoder's last four frames of chunk k-1
+        assert np.array_equal(hdr[k][:, :4].T, pcm_out[k * 5120 - 4: k * 5120])
+    assert np.array_equal(hdr[0][:, :4], np.zeros((channels, 4), dtype=np.int16))  # lms.rs:19-32 initial state
+    assert np.array_equal(hdr[0][:, 4:], np.tile(np.array([0, 0, -8192, 16384], dtype=np.int16), (channels, 1)))
+
+
 def test_golden_fixtures(oracle):
     meta = json.load(open(os.path.join(GOLD, "golden.json")))
     assert len(meta) >= 8
