@@ -4,12 +4,22 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU under torchrun for N > 1)
   python bench.py --impl reference [--gpus N --steps K --warmup W] the reference's own CPU decoder on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic streams.  Headline = batch decode of BASELINE config 4
-(4096 independent stereo 60 s 44.1 kHz CBR-3 streams per GPU, weak scaling: every rank owns its own 4096 streams, nothing is
-exchanged on the data path).  `value` is measured with the .sea bytes already resident in HBM; `e2e` goes through the
-host-buffer C-ABI call (pinned host memory, H2D and D2H inside the timed region).  The same JSON line also carries the encode
-throughput (config 5 shape: 1024 stereo 60 s streams, CBR 3 and VBR 3.0) with its INT32 roofline, the HBM roofline of the
-decode kernel and a CPU baseline timed on this box's host cores.
+A "step" is one pass of the hot path over one batch of synthetic streams.  Headline (`value`) = batch decode of BASELINE
+config 4 (4096 independent stereo 60 s 44.1 kHz CBR-3 streams PER GPU, weak scaling: every rank owns its own 4096 streams,
+nothing is exchanged on the data path), .sea bytes resident in HBM.  The same JSON line carries
+
+  strong        the split the configs themselves state: config 4 = 4096 streams in TOTAL, config 5 = 1024 streams in TOTAL,
+                sharded /N over the ranks (dist.shard_streams), max over ranks
+  sweep         BASELINE config 5: CBR 1..8 and VBR 1.5..7.3 batch encode of the (sharded) 1024 streams, each row with its INT32
+                roofline fraction, its VBR tie count and the decode of what it produced (HBM roofline fraction)
+  e2e           the headline through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region), all
+                streams of the config per step, next to a plain-copy control of the same bytes (frac_of_copy_ceiling)
+  e2e_encode    sea_b200_encode_batch with host buffers, config-5 shape
+  roofline      HBM roofline of the decode kernel; cpu_baseline: the reference's C decoder on this box's host cores
+
+Inputs: every stream is unique (tone + noise, generated on the device by the library's synth kernel, bit-identical to
+sea_codec_b200/synth.py); the encode streams are selected so that the VBR-3 row has no error ties across a bucket boundary
+(where the reference's sort_unstable order -- encoder_vbr.rs:102-103 -- would make "bit-exact" undefined).
 """
 from __future__ import annotations
 
@@ -21,6 +31,7 @@ import sys
 import tempfile
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -29,6 +40,8 @@ sys.path.insert(0, ROOT)
 
 RATE, CHANNELS, SECONDS = 44100, 2, 60
 ALG_OPS_PER_CAND_SAMPLE = 49  # SURVEY.md 8d op count of encoder_base.rs:64-89 + lms.rs
+CBR_ROWS = [1, 2, 3, 4, 5, 6, 7, 8]
+VBR_ROWS = [1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 5.0, 6.0, 7.0, 7.3]
 
 
 def measured_peaks():
@@ -39,6 +52,18 @@ def measured_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"nproc": os.cpu_count(), "usable_cores": host_cores(), "cpu_model": model}
 
 
 def bind_to_gpu_numa_node(index: int) -> None:
@@ -62,15 +87,17 @@ def bind_to_gpu_numa_node(index: int) -> None:
 
 def ncu_traffic(streams: int, seconds: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per launch, from the committed `ncu --set full` capture
-    (profiles/r01_decode_traffic.json: bytes per stream of the 60 s config-4 shape); None when the shape differs."""
-    p = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
-    try:
-        t = json.load(open(p))
-        if seconds != t["seconds"]:
-            return None
-        return float(t["dram_bytes_per_launch"]) / t["streams"] * streams
-    except Exception:
-        return None
+    (profiles/r0X_decode_traffic.json: bytes per stream of the 60 s config-4 shape); None when the shape differs."""
+    for name in ("r02_decode_traffic.json", "r01_decode_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            t = json.load(open(p))
+            if seconds != t["seconds"]:
+                return None
+            return float(t["dram_bytes_per_launch"]) / t["streams"] * streams
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -176,8 +203,9 @@ def reference_arm(args, info):
         "impl": "reference", "metric": "decode_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": workload_config(args, 0),
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": r["kind"], "sample": sample},
+        "host": host_info(),
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -200,14 +228,41 @@ def r_again(prev, cores, reps):
     return out
 
 
-def workload_config(args, unique):
+def workload_config(args):
     return {"workload": f"config4: batch decode of {args.streams} independent stereo {args.seconds} s 44.1 kHz CBR-3 .sea streams "
                         f"per GPU (chunk 5120, sf bits 4, sf frames 20); weak scaling, streams sharded by rank, no collectives",
             "streams_per_gpu": args.streams, "seconds": args.seconds, "sample_rate": RATE, "channels": CHANNELS,
-            "unique_streams": unique, "l2": "inputs larger than L2 (no flush needed)"}
+            "unique_streams": args.streams, "l2": "inputs larger than L2 (no flush needed)"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+
+class Batch:
+    """A batch of equally long streams resident on the device: PCM [n][spp] and, once encoded, .sea [n][stride]."""
+
+    def __init__(self, torch, dev, n, frames, channels):
+        self.n, self.frames, self.channels, self.spp = n, frames, channels, frames * channels
+        self.pcm = torch.empty(n * self.spp, dtype=torch.int16, device=dev)
+        self.pcm_off = np.arange(n, dtype=np.uint64) * self.spp
+        self.nframes = np.full(n, frames, dtype=np.uint32)
+
+
+def encode_device(ctx, torch, dev, b: Batch, n, settings, rate, out=None):
+    """Device-resident batch encode of the first n streams of b; returns (sea tensor, stride, lens, kernel ms)."""
+    bound = ctx.encode_bound(b.frames, b.channels, settings)
+    stride = (bound + 15) // 16 * 16
+    if out is None or out.numel() < n * stride:
+        out = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+    lens = ctx.encode_batch_device(b.pcm.data_ptr(), b.pcm_off[:n], b.nframes[:n], rate, b.channels, settings, out.data_ptr(),
+                                   np.arange(n, dtype=np.uint64) * stride)
+    return out, stride, lens, ctx.last_kernel_ms
+
+
+def decode_device(ctx, sea, stride, lens, headers, pcm_out, spp, n):
+    got = ctx.decode_batch_device(sea.data_ptr(), np.arange(n, dtype=np.uint64) * stride, lens[:n], headers[:n], pcm_out.data_ptr(),
+                                  np.arange(n, dtype=np.uint64) * spp)
+    return got, ctx.last_kernel_ms
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -215,13 +270,14 @@ def main():
     ap.add_argument("--steps", type=int, default=40)  # ~0.6 s timed region: enough nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=4096, help="decode streams per GPU (config 4)")
-    ap.add_argument("--enc-streams", type=int, default=1024, help="encode streams per GPU (config 5)")
-    ap.add_argument("--e2e-streams", type=int, default=512, help="streams per step of the host-buffer (e2e) measurement")
+    ap.add_argument("--streams", type=int, default=4096, help="decode streams per GPU (config 4, weak) and in total (strong)")
+    ap.add_argument("--enc-streams", type=int, default=1024, help="encode streams per GPU (config 5, weak) and in total (strong)")
+    ap.add_argument("--e2e-streams", type=int, default=512, help="streams per host-buffer call (a step loops over all streams)")
     ap.add_argument("--seconds", type=int, default=SECONDS)
-    ap.add_argument("--unique", type=int, default=32, help="distinct synthetic streams generated per GPU (then replicated)")
-    ap.add_argument("--skip-encode", action="store_true")
+    ap.add_argument("--skip-encode", action="store_true", help="skip the encode / sweep / secondary decode sections")
+    ap.add_argument("--skip-sweep", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
 
     from sea_codec_b200 import dist
@@ -235,7 +291,6 @@ def main():
     import torch
 
     import sea_codec_b200 as S
-    from sea_codec_b200 import synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsea_b200 has no CPU fallback (use --impl reference for the CPU arm)")
@@ -244,36 +299,51 @@ def main():
     dev = torch.device("cuda", info.local_rank)
     ctx = S.Context(info.local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    settings = S.EncoderSettings()  # CBR 3, chunk 5120, sf bits 4, sf frames 20
+    W = info.world
+    cbr3 = S.EncoderSettings()  # CBR 3, chunk 5120, sf bits 4, sf frames 20
+    vbr3 = S.EncoderSettings(residual_bits=3.0, vbr=True)
     frames = args.seconds * RATE
-    unique = min(args.unique, args.streams)
-    assert args.streams % unique == 0 and args.enc_streams % unique == 0 and args.e2e_streams % unique == 0
+    n, ns = args.streams, min(args.enc_streams, args.streams)
+    peaks, peak_src = measured_peaks()
+    hbm = peaks["hbm_gbs"]
 
-    # ---- build the inputs on the device: synthetic PCM -> (our encoder) -> .sea streams, replicated to the batch size
-    first, _ = dist.weak_streams(unique, info.rank)
-    pcm_u = synth.gen_batch_torch(unique, frames, CHANNELS, RATE, dev, first_stream=first)
-    bound = ctx.encode_bound(frames, CHANNELS, settings)
-    stride = (bound + 15) // 16 * 16
-    sea_u = torch.zeros(unique * stride, dtype=torch.uint8, device=dev)
-    lens_u = ctx.encode_batch_device(pcm_u.data_ptr(), np.arange(unique) * frames * CHANNELS, np.full(unique, frames), RATE, CHANNELS,
-                                     settings, sea_u.data_ptr(), np.arange(unique) * stride)
-    assert np.all(lens_u == bound)
-    n = args.streams
-    sea = sea_u.view(unique, stride).repeat(n // unique, 1).contiguous().view(-1)
-    headers = np.tile(sea_u.view(unique, stride)[:, :22].cpu().numpy(), (n // unique, 1))
-    sea_off = np.arange(n, dtype=np.uint64) * stride
-    sea_len = np.full(n, bound, dtype=np.uint64)
-    spp = frames * CHANNELS  # samples per stream
+    # ---- inputs: n unique streams per rank, generated on the device.  Stream ids are globally unique (rank * 2^20 + i); the
+    # first ns (the encode batch) are re-drawn until the VBR-3 encode of them has no boundary tie.
+    b = Batch(torch, dev, n, frames, CHANNELS)
+    spp = b.spp
+    ids = (info.rank << 20) + np.arange(n, dtype=np.uint32)
+    torch.cuda.synchronize()
+    ctx.synth_pcm_device(b.pcm.data_ptr(), spp, ids, frames, CHANNELS, RATE)
+    tie_rounds, redrawn, fresh = 0, 0, (info.rank << 20) + (1 << 19)
+    sea_v = None
+    if not args.skip_encode:
+        for tie_rounds in range(1, 13):
+            sea_v, stride_v, lens_v, _ = encode_device(ctx, torch, dev, b, ns, vbr3, RATE, sea_v)
+            per = ctx.last_vbr_ties_per_stream(ns)
+            bad = np.nonzero(per)[0]
+            if bad.size == 0:
+                break
+            for i in bad:
+                ids[i] = fresh
+                fresh += 1
+            redrawn += int(bad.size)
+            ctx.synth_pcm_device(b.pcm.data_ptr(), spp, ids[:ns], frames, CHANNELS, RATE)
+        assert ctx.last_vbr_ties == 0, "could not draw a tie-free VBR-3 encode batch"
+
+    # ---- config 4 inputs: every stream encoded by this library (CBR 3); 8 of them are checked against the oracle below
+    sea, stride, lens, enc_all_ms = encode_device(ctx, torch, dev, b, n, cbr3, RATE)
+    bound = int(lens[0])
+    assert np.all(lens == bound)
+    headers = sea.view(n, stride)[:, :22].cpu().numpy()
     pcm_out = torch.empty(n * spp, dtype=torch.int16, device=dev)
-    pcm_off = np.arange(n, dtype=np.uint64) * spp
     samples_per_step = n * spp
     alg_bytes = float(n * bound + 2 * samples_per_step)
 
     kernel_ms = []
 
-    def decode_step():
-        got = ctx.decode_batch_device(sea.data_ptr(), sea_off, sea_len, headers, pcm_out.data_ptr(), pcm_off)
-        kernel_ms.append(ctx.last_kernel_ms)
+    def decode_step(m=n):
+        got, ms = decode_device(ctx, sea, stride, lens, headers, pcm_out, spp, m)
+        kernel_ms.append(ms)
         return got
 
     for _ in range(args.warmup):
@@ -295,194 +365,284 @@ def main():
     launches = ctx.launch_count - launches0
     ms_total = dist.max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / args.steps
-    value = info.world * samples_per_step / (ms_per_step * 1e-3) / 1e6
+    value = W * samples_per_step / (ms_per_step * 1e-3) / 1e6
     assert np.all(got == spp)
-
-    # ---- parity spot checks on the benchmarked buffers (replicas identical; one stream vs the CPU oracle below)
-    view = pcm_out.view(n, spp)
-    probe = [unique, n - 1] if n > unique else []
-    for i in probe:
-        assert torch.equal(view[i], view[i % unique]), "replicated streams decoded differently"
-    dec0 = view[0].cpu().numpy()
-    sea0 = sea_u[:bound].cpu().numpy().tobytes()
-
-    # ---- roofline of the decode kernel (HBM): algorithmic bytes / average kernel duration
-    peaks, peak_src = measured_peaks()
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "decode_unrolled_kernel<2,3,pair-repl> (+ decode_staged_kernel<2,0> for the partial last chunks, "
                                           "side stream)",
-                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(n, args.seconds), "peak_source": peak_src,
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": ncu_traffic(n, args.seconds),
+                "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_msamples_per_s": samples_per_step / (k_ms * 1e-3) / 1e6}
 
-    # ---- the VBR twin of the headline (decode_vbr_kernel): same stream shape, VBR 3.0, a quarter of the streams
-    vbr_dec = None
-    if not args.skip_encode:
-        st_v = S.EncoderSettings(residual_bits=3.0, vbr=True)
-        nv = max(unique, n // 4)
-        bound_v = ctx.encode_bound(frames, CHANNELS, st_v)
-        stride_v = (bound_v + 15) // 16 * 16
-        sea_vu = torch.zeros(unique * stride_v, dtype=torch.uint8, device=dev)
-        lens_vu = ctx.encode_batch_device(pcm_u.data_ptr(), np.arange(unique) * frames * CHANNELS, np.full(unique, frames), RATE, CHANNELS,
-                                          st_v, sea_vu.data_ptr(), np.arange(unique) * stride_v)
-        sea_v = sea_vu.view(unique, stride_v).repeat(nv // unique, 1).contiguous().view(-1)
-        hdr_v = np.tile(sea_vu.view(unique, stride_v)[:, :22].cpu().numpy(), (nv // unique, 1))
-        len_v = np.tile(lens_vu, nv // unique)
+    # ---- parity on the benchmarked buffers, rank 0 at every N: 8 streams spread over the batch, GPU encode == oracle encode and
+    # GPU decode == oracle decode (and == the reference's c/sea.h when oracle/_ref is there), bit for bit
+    parity = None
+    view = pcm_out.view(n, spp)
+    if info.rank == 0 and not args.skip_cpu:
+        from oracle import sea_oracle as O
+        from sea_codec_b200 import synth
+
+        probe = sorted(set(int(x) for x in np.linspace(0, n - 1, 8)))
+        host_pcm = {i: b.pcm.view(n, spp)[i].cpu().numpy() for i in probe}
+        host_sea = {i: sea.view(n, stride)[i, :bound].cpu().numpy().tobytes() for i in probe}
+        host_dec = {i: view[i].cpu().numpy() for i in probe}
+        assert np.array_equal(host_pcm[probe[0]], synth.gen_stream(int(ids[probe[0]]), frames, CHANNELS, RATE)), "device synth != host recipe"
+        have_ref = O.have_ref() and frames % 20 == 0
+
+        def check(i):
+            assert O.sea_encode(host_pcm[i], RATE, CHANNELS, O.make_settings(3.0)) == host_sea[i], f"stream {i}: GPU encode != oracle encode"
+            assert np.array_equal(O.sea_decode(host_sea[i]).samples, host_dec[i]), f"stream {i}: GPU decode != oracle decode"
+            return i
+
+        with ThreadPoolExecutor(8) as ex:
+            list(ex.map(check, probe))
+        if have_ref:  # c/sea.h keeps static state: one stream, in this thread
+            assert np.array_equal(O.ref_c_decode(host_sea[probe[-1]]).samples, host_dec[probe[-1]]), "GPU decode != c/sea.h decode"
+        parity = {"streams_checked": probe, "encode_vs_oracle": "bit-exact", "decode_vs_oracle": "bit-exact",
+                  "decode_vs_reference_c": "bit-exact (1 stream)" if have_ref else "not run"}
+        if sea_v is not None:
+            vprobe = sorted(set(int(x) for x in np.linspace(0, ns - 1, 4)))
+            vsea = {i: sea_v.view(-1)[i * stride_v: i * stride_v + int(lens_v[i])].cpu().numpy().tobytes() for i in vprobe}
+            vpcm = {i: b.pcm.view(n, spp)[i].cpu().numpy() for i in vprobe}
+
+            def vcheck(i):
+                ref, ties = O.sea_encode(vpcm[i], RATE, CHANNELS, O.make_settings(3.0, vbr=True), return_ties=True)
+                assert ties == 0 and ref == vsea[i], f"stream {i}: GPU VBR-3 encode != oracle encode"
+
+            with ThreadPoolExecutor(4) as ex:
+                list(ex.map(vcheck, vprobe))
+            parity["vbr3_encode_vs_oracle"] = {"streams_checked": vprobe, "result": "bit-exact", "ties": 0}
+        del host_pcm, host_sea, host_dec
+
+    # ---- strong scaling of config 4: 4096 streams in TOTAL, this rank decodes its shard
+    strong = {}
+    lo, hi = dist.shard_streams(n, info.rank, W)
+    m4 = hi - lo
+    ks = []
+    for _ in range(2 + max(3, min(args.steps, 10))):
+        _, ms = decode_device(ctx, sea, stride, lens, headers, pcm_out, spp, m4)
+        ks.append(ms)
+    ms4 = dist.max_over_ranks(float(np.mean(ks[2:])))
+    strong["decode_config4"] = {"streams_total": n, "streams_per_gpu": m4, "value": n * spp / (ms4 * 1e-3) / 1e6, "unit": "Msamples/s",
+                                "ms_per_step": ms4, "hbm_frac_per_gpu": (m4 * bound + 2.0 * m4 * spp) / (ms4 * 1e-3) / 1e9 / hbm}
+
+    def hbm_row(n_streams, total_bytes, ms, kernel):
+        gbs = total_bytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
+
+    def time_decode(sea_t, stride_t, lens_t, m, spp_t, reps=None):
+        hd = sea_t.view(-1)[: m * stride_t].view(m, stride_t)[:, :22].cpu().numpy()
         ks = []
-        for _ in range(2 + max(3, min(args.steps, 10))):
-            got_v = ctx.decode_batch_device(sea_v.data_ptr(), np.arange(nv, dtype=np.uint64) * stride_v, len_v, hdr_v, pcm_out.data_ptr(),
-                                            pcm_off[:nv])
-            ks.append(ctx.last_kernel_ms)
-        assert np.all(got_v == spp)
-        ms_v = dist.max_over_ranks(float(np.mean(ks[2:])))
-        bytes_v = float(len_v.sum() + 2 * nv * spp)
-        vbr_dec = {"value": info.world * nv * spp / (ms_v * 1e-3) / 1e6, "unit": "Msamples/s", "streams_per_gpu": nv, "ms_per_step": ms_v,
-                   "roofline": {"bound": "hbm", "kernel": "decode_vbr_kernel<2>", "achieved": bytes_v / (ms_v * 1e-3) / 1e9,
-                                "peak": measured_peaks()[0]["hbm_gbs"], "unit": "GB/s",
-                                "frac": bytes_v / (ms_v * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}}
-        del sea_v, sea_vu
+        for _ in range(2 + (reps or max(3, min(args.steps, 10)))):
+            g, ms = decode_device(ctx, sea_t, stride_t, lens_t, hd, pcm_out, spp_t, m)
+            ks.append(ms)
+        assert np.all(g == spp_t)
+        return float(np.mean(ks[2:]))
+
+    # ---- the VBR twin of the headline (decode_vbr_kernel): the tie-free VBR-3 batch, ns streams per GPU
+    vbr_dec = mc_dec = encode = sweep = None
+    if not args.skip_encode:
+        ms_v = dist.max_over_ranks(time_decode(sea_v, stride_v, lens_v, ns, spp))
+        bytes_v = float(lens_v.sum() + 2 * ns * spp)
+        vbr_dec = {"value": W * ns * spp / (ms_v * 1e-3) / 1e6, "unit": "Msamples/s", "streams_per_gpu": ns, "ms_per_step": ms_v,
+                   "roofline": hbm_row(ns, bytes_v, ms_v, "decode_vbr_kernel<2>")}
+
+        # ---- BASELINE config 3 shape (8 channels, 48 kHz, CBR 4): 256 unique 60 s streams through decode_mc_kernel
+        ch8, rate8, fr8, n8 = 8, 48000, args.seconds * 48000, 256
+        b8 = Batch(torch, dev, n8, fr8, ch8)
+        ctx.synth_pcm_device(b8.pcm.data_ptr(), b8.spp, (info.rank << 20) + (1 << 18) + np.arange(n8, dtype=np.uint32), fr8, ch8, rate8)
+        sea8, stride8, lens8, _ = encode_device(ctx, torch, dev, b8, n8, S.EncoderSettings(residual_bits=4.0), rate8)
+        ms8 = dist.max_over_ranks(time_decode(sea8, stride8, lens8, n8, b8.spp))
+        mc_dec = {"value": W * n8 * b8.spp / (ms8 * 1e-3) / 1e6, "unit": "Msamples/s", "streams_per_gpu": n8, "channels": ch8,
+                  "seconds": args.seconds, "ms_per_step": ms8,
+                  "roofline": hbm_row(n8, float(lens8.sum() + 2 * n8 * b8.spp), ms8, "decode_mc_kernel<8,4>")}
+        del b8, sea8
         torch.cuda.empty_cache()
 
-    # ---- BASELINE config 3 shape (8 channels, 48 kHz, CBR 4; multichannel lane mapping): 256 streams of 60 s through decode_mc_kernel
-    mc_dec = None
-    if not args.skip_encode:
-        ch8, rate8, fr8, n8, u8 = 8, 48000, 60 * 48000, 256, 4
-        st8 = S.EncoderSettings(residual_bits=4.0)
-        pcm8 = synth.gen_batch_torch(u8, fr8, ch8, rate8, dev, first_stream=first)
-        b8 = ctx.encode_bound(fr8, ch8, st8)
-        s8 = (b8 + 15) // 16 * 16
-        sea8u = torch.zeros(u8 * s8, dtype=torch.uint8, device=dev)
-        ctx.encode_batch_device(pcm8.data_ptr(), np.arange(u8) * fr8 * ch8, np.full(u8, fr8), rate8, ch8, st8, sea8u.data_ptr(),
-                                np.arange(u8) * s8)
-        sea8 = sea8u.view(u8, s8).repeat(n8 // u8, 1).contiguous().view(-1)
-        hdr8 = np.tile(sea8u.view(u8, s8)[:, :22].cpu().numpy(), (n8 // u8, 1))
-        spp8 = fr8 * ch8
-        ks = []
-        for _ in range(2 + max(3, min(args.steps, 10))):
-            got8 = ctx.decode_batch_device(sea8.data_ptr(), np.arange(n8, dtype=np.uint64) * s8, np.full(n8, b8, dtype=np.uint64), hdr8,
-                                           pcm_out.data_ptr(), np.arange(n8, dtype=np.uint64) * spp8)
-            ks.append(ctx.last_kernel_ms)
-        assert np.all(got8 == spp8)
-        ms8 = dist.max_over_ranks(float(np.mean(ks[2:])))
-        bytes8 = float(n8 * b8 + 2 * n8 * spp8)
-        mc_dec = {"value": info.world * n8 * spp8 / (ms8 * 1e-3) / 1e6, "unit": "Msamples/s", "streams_per_gpu": n8, "channels": ch8,
-                  "seconds": 60, "ms_per_step": ms8,
-                  "roofline": {"bound": "hbm", "kernel": "decode_mc_kernel<8,4>", "achieved": bytes8 / (ms8 * 1e-3) / 1e9,
-                               "peak": measured_peaks()[0]["hbm_gbs"], "unit": "GB/s",
-                               "frac": bytes8 / (ms8 * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}}
-        del pcm8, sea8, sea8u
-        torch.cuda.empty_cache()
-
-    # ---- e2e: the same decode through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
-    ne = min(args.e2e_streams, n)
-    while True:  # pinned host memory is a shared resource on a multi-GPU box: shrink the sample rather than fail
-        try:
-            h_sea = torch.empty(ne * stride, dtype=torch.uint8).pin_memory()
-            h_pcm = torch.empty(ne * spp, dtype=torch.int16).pin_memory()
-            break
-        except RuntimeError:
-            if ne <= unique:
-                raise
-            ne = max(unique, ne // 2 // unique * unique)
-    h_sea.copy_(sea[: ne * stride])
-    torch.cuda.synchronize()
-
-    def e2e_step():
-        return ctx.decode_batch_host(h_sea.data_ptr(), sea_off[:ne], sea_len[:ne], h_pcm.data_ptr(), pcm_off[:ne])
-
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    dist.barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = dist.max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    assert np.array_equal(h_pcm[:spp].numpy(), dec0), "host-buffer decode differs from the device-resident decode"
-    e2e = {"value": info.world * ne * spp / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(ne * bound),
-           "d2h_bytes_per_step": int(ne * spp * 2), "ms_per_step": e2e_s * 1e3,
-           "sample": f"{ne} of the {n} streams per step (bounded pinned-host footprint); PCIe-bound"}
-    del h_sea, h_pcm, pcm_out, view
-    torch.cuda.empty_cache()
-
-    # ---- encode (config 5 shape): CBR 3 and VBR 3.0, INT32 roofline
-    encode = None
-    if not args.skip_encode:
-        ops_peak, _ = max((ctx.int32_peak(m) for m in (0, 1, 2)), key=lambda t: t[0])
+        # ---- encode, config-5 shape.  INT32 roofline: measured two-pipe issue peak (sea_b200_int32_peak)
         peaks_int = {m: ctx.int32_peak(m)[0] for m in (0, 1, 2)}
-        ns = args.enc_streams
-        pcm_e = pcm_u.repeat(ns // unique, 1).contiguous().view(-1)
-        out_e = torch.zeros(ns * ((max(bound, ctx.encode_bound(frames, CHANNELS, S.EncoderSettings(residual_bits=3.0, vbr=True))) + 15) // 16 * 16),
-                            dtype=torch.uint8, device=dev)
-        estride = out_e.numel() // ns
-        encode = {"streams_per_gpu": ns, "int32_peak_lane_ops_per_s": {"imad": peaks_int[0], "lop3": peaks_int[1], "mixed": peaks_int[2]}}
-        for name, st_e, passes in (("cbr3", settings, 1), ("vbr3", S.EncoderSettings(residual_bits=3.0, vbr=True), 2)):
-            def enc_step():
-                return ctx.encode_batch_device(pcm_e.data_ptr(), np.arange(ns) * spp, np.full(ns, frames), RATE, CHANNELS, st_e,
-                                               out_e.data_ptr(), np.arange(ns) * estride)
-            enc_step()
-            dist.barrier()
-            torch.cuda.synchronize()
+        ops_peak = max(peaks_int.values())
+        scratch = torch.zeros(ns * ((ctx.encode_bound(frames, CHANNELS, S.EncoderSettings(residual_bits=8.0)) + 15) // 16 * 16),
+                              dtype=torch.uint8, device=dev)
+
+        def time_encode(st_e, m, reps):
+            out, stride_e, lens_e, _ = encode_device(ctx, torch, dev, b, m, st_e, RATE, scratch)  # warm-up
             ks = []
-            steps_e = max(1, min(args.steps, 3))
-            for _ in range(steps_e):
-                elens = enc_step()
-                ks.append(ctx.last_kernel_ms)
-            ms_e = dist.max_over_ranks(float(np.mean(ks)))
-            sps = info.world * ns * spp / (ms_e * 1e-3)
+            for _ in range(reps):
+                out, stride_e, lens_e, ms = encode_device(ctx, torch, dev, b, m, st_e, RATE, scratch)
+                ks.append(ms)
+            return float(np.mean(ks)), out, stride_e, lens_e
+
+        def int_row(sps_per_gpu, passes):
             ops = ALG_OPS_PER_CAND_SAMPLE * 16 * passes  # 49 * 2^sf_bits * passes
-            encode[name] = {"value": sps / 1e6, "unit": "Msamples/s", "ms_per_step": ms_e, "bytes_per_stream": int(elens[0]),
-                            "vbr_ties": ctx.last_vbr_ties,
-                            "roofline": {"bound": "int32", "achieved": sps / info.world * ops / 1e12, "peak": ops_peak / 1e12,
-                                         "unit": "Tops/s", "frac": sps / info.world * ops / ops_peak, "ops_per_sample": ops}}
-        del pcm_e, out_e
+            return {"bound": "int32", "achieved": sps_per_gpu * ops / 1e12, "peak": ops_peak / 1e12, "unit": "Tops/s",
+                    "frac": sps_per_gpu * ops / ops_peak, "ops_per_sample": ops}
+
+        encode = {"streams_per_gpu": ns, "int32_peak_lane_ops_per_s": {"imad": peaks_int[0], "lop3": peaks_int[1], "mixed": peaks_int[2]},
+                  "tie_free_selection": {"rounds": tie_rounds, "streams_redrawn": redrawn, "of": ns}}
+        reps_e = max(1, min(args.steps, 3))
+        for name, st_e, passes in (("cbr3", cbr3, 1), ("vbr3", vbr3, 2)):  # weak: ns streams on every GPU
+            dist.barrier()
+            ms_e, _, _, lens_e = time_encode(st_e, ns, reps_e)
+            ties_e = ctx.last_vbr_ties
+            ms_e = dist.max_over_ranks(ms_e)
+            encode[name] = {"value": W * ns * spp / (ms_e * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_e,
+                            "bytes_per_stream": int(lens_e[0]), "vbr_ties": int(dist.sum_over_ranks(ties_e)),
+                            "roofline": int_row(ns * spp / (ms_e * 1e-3), passes)}
+        # the machine full: every stream of the decode batch (n per GPU, 60 s) through the same kernel -- timed while building config 4
+        encode["cbr3_all_streams"] = {"value": W * n * spp / (dist.max_over_ranks(enc_all_ms) * 1e-3) / 1e6, "unit": "Msamples/s",
+                                      "ms_per_step": enc_all_ms, "streams_per_gpu": n, "seconds": args.seconds,
+                                      "roofline": int_row(n * spp / (enc_all_ms * 1e-3), 1)}
+
+        # ---- BASELINE config 5 as stated: ns streams in TOTAL sharded /N, every CBR and VBR bitrate; each row also decodes what it made
+        lo5, hi5 = dist.shard_streams(ns, info.rank, W)
+        m5 = hi5 - lo5  # this rank's shard = the first m5 of its own (tie-free) streams
+        if not args.skip_sweep and m5 > 0:
+            sweep = {"streams_total": ns, "streams_per_gpu": m5, "seconds": args.seconds, "rows": []}
+            rows = [("cbr", float(r), S.EncoderSettings(residual_bits=float(r)), 1) for r in CBR_ROWS] + \
+                   [("vbr", r, S.EncoderSettings(residual_bits=r, vbr=True), 2) for r in VBR_ROWS]
+            for mode, bits, st_e, passes in rows:
+                ms_e, out, stride_e, lens_e = time_encode(st_e, m5, 2)
+                ties_e = ctx.last_vbr_ties if mode == "vbr" else 0
+                ms_d = time_decode(out, stride_e, lens_e, m5, spp, reps=3)
+                ms_e, ms_d = dist.max_over_ranks(ms_e), dist.max_over_ranks(ms_d)
+                tot_bytes = dist.sum_over_ranks(float(lens_e.sum()))
+                row = {"mode": mode, "residual_bits": bits, "bits_per_sample": 8.0 * tot_bytes / (ns * spp),
+                       "encode_msamples_per_s": ns * spp / (ms_e * 1e-3) / 1e6, "encode_ms": ms_e,
+                       "encode_int32_frac_per_gpu": m5 * spp / (ms_e * 1e-3) * ALG_OPS_PER_CAND_SAMPLE * 16 * passes / ops_peak,
+                       "decode_msamples_per_s": ns * spp / (ms_d * 1e-3) / 1e6, "decode_ms": ms_d,
+                       "decode_hbm_frac_per_gpu": (float(lens_e.sum()) + 2.0 * m5 * spp) / (ms_d * 1e-3) / 1e9 / hbm,
+                       "vbr_ties": int(dist.sum_over_ranks(ties_e))}
+                sweep["rows"].append(row)
+                if mode == "cbr" and bits == 3.0:
+                    strong["encode_config5_cbr3"] = {"streams_total": ns, "streams_per_gpu": m5, "value": row["encode_msamples_per_s"],
+                                                     "unit": "Msamples/s", "ms_per_step": ms_e, "int32_frac_per_gpu": row["encode_int32_frac_per_gpu"]}
+                if mode == "vbr" and bits == 3.0:
+                    strong["encode_config5_vbr3"] = {"streams_total": ns, "streams_per_gpu": m5, "value": row["encode_msamples_per_s"],
+                                                     "unit": "Msamples/s", "ms_per_step": ms_e, "int32_frac_per_gpu": row["encode_int32_frac_per_gpu"],
+                                                     "vbr_ties": row["vbr_ties"]}
+            sweep["note"] = ("VBR rows other than 3.0 report the ties their own rank order produces on these inputs: on those chunks the "
+                             "reference's sort_unstable order (encoder_vbr.rs:102-103) is unspecified and parity vs the Rust crate undefined")
+        del scratch
         torch.cuda.empty_cache()
-        # the same kernel with the machine full: 4096 streams of 10 s (one warp per stream: 1024 streams leave the SMs latency-bound)
-        nl, fl_ = 4 * ns, 10 * RATE
-        pcm_l = pcm_u.view(unique, frames, CHANNELS)[:, :fl_, :].repeat(nl // unique, 1, 1).contiguous().view(-1)
-        bl = ctx.encode_bound(fl_, CHANNELS, settings)
-        sl = (bl + 15) // 16 * 16
-        out_l = torch.zeros(nl * sl, dtype=torch.uint8, device=dev)
-        ks = []
-        for _ in range(3):
-            ctx.encode_batch_device(pcm_l.data_ptr(), np.arange(nl) * fl_ * CHANNELS, np.full(nl, fl_), RATE, CHANNELS, settings,
-                                    out_l.data_ptr(), np.arange(nl) * sl)
-            ks.append(ctx.last_kernel_ms)
-        ms_l = dist.max_over_ranks(float(np.mean(ks[1:])))
-        sps_l = info.world * nl * fl_ * CHANNELS / (ms_l * 1e-3)
-        encode["cbr3_4096_streams"] = {"value": sps_l / 1e6, "unit": "Msamples/s", "ms_per_step": ms_l, "streams_per_gpu": nl, "seconds": 10,
-                                       "roofline": {"bound": "int32", "achieved": sps_l / info.world * 784 / 1e12, "peak": ops_peak / 1e12,
-                                                    "unit": "Tops/s", "frac": sps_l / info.world * 784 / ops_peak, "ops_per_sample": 784}}
-        del pcm_l, out_l
-        torch.cuda.empty_cache()
+
+    # ---- e2e: the headline through the host-buffer C-ABI call.  A step = ALL n streams, as n / ne calls over the same pinned
+    # buffers (bounded pinned-host footprint), H2D + D2H inside the timed region.  Control: plain copies of the same bytes.
+    e2e = {"value": None, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    e2e_encode = None
+    if not args.skip_e2e:
+        ne = min(args.e2e_streams, n)
+        while n % ne:
+            ne -= 1
+        while True:  # pinned host memory is a shared resource on a multi-GPU box: shrink the call size rather than fail
+            try:
+                h_sea = torch.empty(ne * stride, dtype=torch.uint8).pin_memory()
+                h_pcm = torch.empty(ne * spp, dtype=torch.int16).pin_memory()
+                break
+            except RuntimeError:
+                if ne <= 16:
+                    raise
+                ne //= 2
+                while n % ne:
+                    ne -= 1
+        calls = n // ne
+        h_sea.copy_(sea[: ne * stride])
+        torch.cuda.synchronize()
+        sea_off_e, sea_len_e, pcm_off_e = np.arange(ne, dtype=np.uint64) * stride, lens[:ne], np.arange(ne, dtype=np.uint64) * spp
+
+        def e2e_step():
+            for _ in range(calls):
+                ctx.decode_batch_host(h_sea.data_ptr(), sea_off_e, sea_len_e, h_pcm.data_ptr(), pcm_off_e)
+
+        ctx.decode_batch_host(h_sea.data_ptr(), sea_off_e, sea_len_e, h_pcm.data_ptr(), pcm_off_e)  # warm-up: buffers, both lanes
+        dist.barrier()
+        e2e_steps = max(2, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = dist.max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        dec0 = view[0].cpu().numpy()
+        assert np.array_equal(h_pcm[:spp].numpy(), dec0), "host-buffer decode differs from the device-resident decode"
+        # control: the same byte counts as plain cudaMemcpyAsync, H2D and D2H on two streams at once, all ranks at the same time
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        d_in, d_out = sea[: ne * stride], pcm_out[: ne * spp]
+
+        def copy_step():
+            for _ in range(calls):
+                with torch.cuda.stream(s_up):
+                    d_in.copy_(h_sea, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_pcm.copy_(d_out, non_blocking=True)
+
+        copy_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_step()
+        torch.cuda.synchronize()
+        copy_s = dist.max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": W * n * spp / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(n * bound),
+               "d2h_bytes_per_step": int(n * spp * 2), "ms_per_step": e2e_s * 1e3,
+               "calls_per_step": calls, "streams_per_call": ne,
+               "copy_ceiling_ms": copy_s * 1e3, "copy_ceiling_gbs_per_gpu": (n * bound + n * spp * 2) / copy_s / 1e9,
+               "frac_of_copy_ceiling": copy_s / e2e_s,
+               "sample": f"all {n} streams per step as {calls} calls of {ne} streams over the same pinned buffers; PCIe-bound"}
+        # ---- e2e encode: sea_b200_encode_batch, host PCM in (2 B/sample), .sea out; a step = ns streams as ns / ne_e calls
+        if not args.skip_encode:
+            ne_e = min(ne, ns)
+            while ns % ne_e:
+                ne_e -= 1
+            calls_e = ns // ne_e
+            h_pcm[: ne_e * spp].copy_(b.pcm[: ne_e * spp])
+            torch.cuda.synchronize()
+            out_off_e = np.arange(ne_e, dtype=np.uint64) * stride
+
+            def enc_e2e_step():
+                for _ in range(calls_e):
+                    got_l = ctx.encode_batch_host(h_pcm.data_ptr(), pcm_off_e[:ne_e], b.nframes[:ne_e], RATE, CHANNELS, cbr3, h_sea.data_ptr(),
+                                                  out_off_e)
+                return got_l
+
+            enc_e2e_step()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                got_l = enc_e2e_step()
+            enc_s = dist.max_over_ranks(time.perf_counter() - t0) / 2
+            assert np.all(got_l == bound)
+            assert torch.equal(h_sea[:bound], sea[:bound].cpu()), "host-buffer encode differs from the device-resident encode"
+            e2e_encode = {"value": W * ns * spp / enc_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(ns * spp * 2),
+                          "d2h_bytes_per_step": int(ns * bound), "ms_per_step": enc_s * 1e3, "calls_per_step": calls_e,
+                          "streams_per_call": ne_e, "workload": "config-5 shape, CBR 3"}
+        del h_sea, h_pcm
+    del pcm_out, view
+    torch.cuda.empty_cache()
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same stream shape
     cpu = None
-    if info.rank == 0 and info.world == 1 and not args.skip_cpu:
+    if info.rank == 0 and W == 1 and not args.skip_cpu:
         from oracle import sea_oracle as O
 
         cores = host_cores()
         reps = 4
         r = cpu_decode_baseline(cores, reps, args.seconds)
-        if args.seconds == SECONDS:  # the oracle checks stream 0 of the benchmarked batch, bit for bit
-            assert r["sea"] == sea0, "GPU-encoded stream 0 differs from the oracle's encode"
-        assert np.array_equal(O.sea_decode(sea0).samples, dec0), "GPU-decoded stream 0 differs from the oracle's decode"
         e_secs, e_samples = O.bench("encode", cores, 1, r["pcm"], RATE, CHANNELS, r["settings"])
         cpu = {"value": r["value"], "unit": "Msamples/s", "cores": cores, "kind": r["kind"],
                "sample": f"{cores} cores x {reps} decodes of one {args.seconds} s stereo CBR-3 stream (config-4 stream shape)",
                "encode_cbr3_msamples_per_s": e_samples / e_secs / 1e6, "encode_kind": "port",
-               "encode_sample": f"{cores} cores x 1 encode of the same stream (oracle restatement; no Rust toolchain)",
-               "parity_checked": "stream 0 of the benchmarked batch: GPU encode == oracle encode, GPU decode == oracle decode"}
+               "encode_sample": f"{cores} cores x 1 encode of the same stream (oracle restatement; no Rust toolchain)"}
 
     if info.rank == 0:
         print(json.dumps({
-            "metric": "decode_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": info.world, "steps": args.steps,
+            "metric": "decode_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": W, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "i32", "data": "synthetic", "config": workload_config(args, unique), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode_vbr3": vbr_dec, "decode_8ch_cbr4": mc_dec, "encode": encode,
+            "dtype": "i32", "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "host": host_info(), "parity": parity,
+            "strong": strong, "decode_vbr3": vbr_dec, "decode_8ch_cbr4": mc_dec, "encode": encode, "e2e_encode": e2e_encode,
+            "sweep": sweep,
         }))
     ctx.close()
     dist.shutdown()
