@@ -379,6 +379,7 @@ def main():
     # GPU decode == oracle decode (and == the reference's c/sea.h when oracle/_ref is there), bit for bit
     parity = None
     view = pcm_out.view(n, spp)
+    dec0 = view[0].cpu().numpy()  # kept for the host-buffer comparison below (pcm_out is reused by the other sections)
     if info.rank == 0 and not args.skip_cpu:
         from oracle import sea_oracle as O
         from sea_codec_b200 import synth
@@ -563,7 +564,6 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = dist.max_over_ranks(time.perf_counter() - t0) / e2e_steps
-        dec0 = view[0].cpu().numpy()
         assert np.array_equal(h_pcm[:spp].numpy(), dec0), "host-buffer decode differs from the device-resident decode"
         # control: the same byte counts as plain cudaMemcpyAsync, H2D and D2H on two streams at once, all ranks at the same time
         s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
