@@ -105,19 +105,22 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
                  const int32_t *__restrict__ tab, int *err)
 {
     using Cfg = MCfg<CT, B>;
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t s = 4;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
-    // dequant rows of size B as uploaded: lut[sf][code]
-    int32_t *lut = reinterpret_cast<int32_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
+    // dequant rows of size B as uploaded: lut[sf][code], at the start of the (1024-byte aligned) shared window so that a row's
+    // base address has its low B + 2 bits clear and "row | code << 2" needs no add
+    const uint32_t nwarps = blockDim.x >> 5;  // chosen per launch (launch_mc): fewer warps per CTA when the grid is only a few waves
+    const uint32_t smem_sh = smem_u32m(smem), lut_sh = (smem_sh + 1023u) & ~1023u;
+    int32_t *lut = reinterpret_cast<int32_t *>(smem + (lut_sh - smem_sh));
     for (uint32_t i = threadIdx.x; i < (1u << (s + B)); i += blockDim.x) lut[i] = tab[tab_dqt_off(s, B) + i];
     __syncthreads();
-    const uint32_t lut_sh = smem_u32m(lut);
+    const uint32_t rings_off = (lut_sh - smem_sh) + (4u << (s + B));
 
     constexpr int CPL = Cfg::CPL;
     const uint32_t pr = lane % Cfg::U;                              // my channel group (pair or quad)
-    uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kChunksPerWarp + lane / Cfg::U;  // global chunk index
+    uint64_t g = ((uint64_t)blockIdx.x * nwarps + warp) * Cfg::kChunksPerWarp + lane / Cfg::U;  // global chunk index
     const bool valid = lane < (uint32_t)(Cfg::kChunksPerWarp * Cfg::U) && g < p.total_chunks;
     if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
 
@@ -149,7 +152,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     // ---- per-lane ring.  Word w of the 16-byte aligned stream sits at ring word (w & 63).
     const uint64_t a0 = res_off & ~(uint64_t)15;
     const uint8_t *src0 = sea + a0;
-    const uint32_t ring_sh = smem_u32m(smem + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
+    const uint32_t ring_sh = smem_u32m(smem + rings_off + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
     uint32_t fetched = 0;                                        // granules issued so far
     uint32_t posg = (uint32_t)(res_off - a0) * 8u;               // bit position of the current body's first field, from a0
 #pragma unroll
@@ -230,15 +233,19 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
             int32_t y[CPL], d[CPL], sgn[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; c++) {
-                uint32_t code;
+                // the code lands at bit 2 (the table's 4-byte stride) in ONE shift; mask and row base join it in one LOP3
+                uint32_t code4;
+                constexpr uint32_t kMask4 = ((1u << B) - 1u) << 2;
                 if (kGB <= 32) {
-                    code = (x >> (B * (CPL - 1 - c))) & ((1u << B) - 1u);
+                    const int sh2 = B * (CPL - 1 - c) - 2;
+                    code4 = sh2 >= 0 ? (x >> (sh2 & 31)) : (x << ((-sh2) & 31));
                 } else {  // wider groups: every field on its own, still at a compile-time position
                     const int cb = bit + c * B, cw = cb >> 5, co = cb & 31;
-                    if (co + B <= 32) code = (W[cw] >> (32 - co - B)) & ((1u << B) - 1u);
-                    else code = __funnelshift_r(W[cw + 1], W[cw], (64 - co - B) & 31) & ((1u << B) - 1u);
+                    if (co + B + 2 <= 32) code4 = W[cw] >> (32 - co - B - 2);
+                    else if (co + B <= 32) code4 = W[cw] << ((co + B + 2 - 32) & 31);
+                    else code4 = __funnelshift_r(W[cw + 1], W[cw], (64 - co - B - 2) & 31);
                 }
-                d[c] = lds_s32m(rowbase[c] + code * 4u);
+                d[c] = lds_s32m((code4 & kMask4) | rowbase[c]);
                 const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                      (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                 y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:38, before the clamp
@@ -306,12 +313,14 @@ static cudaError_t launch_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStre
                              int *d_err, cudaStream_t stream)
 {
     using Cfg = MCfg<CT, B>;
-    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + ((size_t)4u << (4 + B));
-    cudaError_t e = cudaFuncSetAttribute(decode_mc_kernel<CT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint32_t warps = pick_cta_warps(p.total_chunks, Cfg::kChunksPerWarp, Cfg::kWarps);
+    const size_t smem = (size_t)warps * Cfg::kWarpBytes + ((size_t)4u << (4 + B)) + 1024u;
+    cudaError_t e = cudaFuncSetAttribute(decode_mc_kernel<CT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)Cfg::kWarps * Cfg::kWarpBytes + ((size_t)4u << (4 + B)) + 1024u));
     if (e != cudaSuccess) return e;
-    const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kChunksPerWarp;
+    const uint64_t chunks_per_cta = (uint64_t)warps * Cfg::kChunksPerWarp;
     const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
-    decode_mc_kernel<CT, B><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    decode_mc_kernel<CT, B><<<(unsigned)blocks, warps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
     return cudaGetLastError();
 }
 

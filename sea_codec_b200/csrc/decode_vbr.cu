@@ -36,10 +36,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int32_t lds_s32v(uint32_t addr)
+__device__ __forceinline__ int32_t lds_s16v(uint32_t addr)
 {
     int32_t v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void st_global_256v(void *p, const uint32_t (&v)[8])
@@ -77,9 +77,11 @@ struct VCfg {
 
 }  // namespace
 
-// RS = log2 of the replication of every table entry (copy lane & (2^RS - 1) is the one a lane reads).  The dependent look-up is
-// the busiest shared-memory access (un-replicated ~2.5 wavefronts per load, LSU data pipe 83 %), yet RS = 3 measured slower than
-// RS = 0 (see launch_decode_vbr), so RS = 0 is what runs.
+// The dependent look-up is the busiest shared-memory access of this kernel: with the rows as uploaded (4-byte entries, one copy)
+// a warp's 32 look-ups cost ~2.5 wavefronts and the LSU data pipe ran 83 % busy with 60 % of its wavefronts excess
+// (profiles/r02_dec_vbr3_*).  Every dequantised value fits 16 bits (|d| <= 255 * 99, dqt.rs), so the table is held as int16 and
+// every entry is replicated 2^RS times (copy lane & (2^RS - 1) is the one a lane reads): RS = 5 -- a copy per lane, two lanes per
+// bank word -- leaves at most 2-way conflicts; the launcher picks the largest RS whose table fits next to the rings.
 template <int C, int RS>
 __global__ void __launch_bounds__(VCfg<C>::kWarps * 32, 1)
 decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams, DecFastParams p,
@@ -94,10 +96,10 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
 
     // ---- dequant rows of sizes lo_size..hi_size, contiguous in the uploaded table (sea_common.cuh: tab_dqt_off)
     const uint32_t lut_words = tab_dqt_off(s, hi_size + 1u) - tab_dqt_off(s, lo_size);
-    int32_t *lut = reinterpret_cast<int32_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
-    for (uint32_t i = threadIdx.x; i < (lut_words << RS); i += blockDim.x) lut[i] = tab[tab_dqt_off(s, lo_size) + (i >> RS)];
+    int16_t *lut = reinterpret_cast<int16_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
+    for (uint32_t i = threadIdx.x; i < (lut_words << RS); i += blockDim.x) lut[i] = (int16_t)tab[tab_dqt_off(s, lo_size) + (i >> RS)];
     __syncthreads();
-    const uint32_t lut_sh = smem_u32v(lut) + (lane & ((1u << RS) - 1u)) * 4u;
+    const uint32_t lut_sh = smem_u32v(lut) + (lane & ((1u << RS) - 1u)) * 2u;
 
     uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + lane;  // global chunk index
     const bool valid = g < p.total_chunks;
@@ -193,7 +195,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
                     const uint32_t sz = ((sz4 >> (6 - 2 * item)) & 3u) + hb - 1u;  // chunk.rs:136-138
                     bad |= sz < 1u || sz > 8u;
                     size[c] = sz < lo_size ? lo_size : (sz > hi_size ? hi_size : sz);  // keeps the look-up inside the table
-                    rowbase[c] = lut_sh + (((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) << (2 + RS));
+                    rowbase[c] = lut_sh + (((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) << (1 + RS));
                     st_bits += size[c];
                 }
                 const uint32_t sh_frame = 32u - st_bits;      // frame field (both channels) -> low bits
@@ -214,7 +216,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
 #pragma unroll
                         for (int c = 0; c < C; c++) {
                             const uint32_t code = (c == C - 1) ? (x & m_last) : (x >> size[C - 1]);
-                            d[c] = lds_s32v(rowbase[c] + (code << (2 + RS)));
+                            d[c] = lds_s16v(rowbase[c] + (code << (1 + RS)));
                             const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                                  (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                             y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:74, before the clamp
@@ -276,7 +278,7 @@ static cudaError_t launch_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStr
                               int *d_err, size_t lut_bytes, cudaStream_t stream)
 {
     using Cfg = VCfg<C>;
-    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + (lut_bytes << RS);
+    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + ((lut_bytes / 2u) << RS);
     cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
@@ -292,15 +294,30 @@ cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStr
     const int32_t *tab = tabs.by_s[p.s];
     const uint32_t lo = p.b > 1u ? p.b - 1u : 1u, hi = p.b + 2u < 8u ? p.b + 2u : 8u;
     const size_t lut_bytes = (size_t)(tab_dqt_off(4, hi + 1u) - tab_dqt_off(4, lo)) * 4u;
-    // Measured (1024 stereo VBR-3 streams): replicated 5.03 ms, plain 4.86 ms -- the plain table is the default;
-    // SEA_B200_VBR_REP=1 selects the replicated one for tuning runs.
-    const char *env = getenv("SEA_B200_VBR_REP");
-    const bool rep = env && env[0] == '1' && lut_bytes * 8u <= 48u * 1024u;
-    if (p.channels == 1)
-        return rep ? launch_vbr<1, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream)
-                   : launch_vbr<1, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);
-    return rep ? launch_vbr<2, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream)
-               : launch_vbr<2, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);
+    // int16 entries, 2^RS copies.  Measured (1024 stereo 60 s streams, profiles/r02_probe2.txt): VBR-3 RS 0 / 3 / 4 / 5 = 4.75 /
+    // 5.01 / 5.07 / 4.78 ms, VBR-5.5 4.99 / 5.33 / 5.51 / 5.52 ms -- the bank conflicts are not what bounds the kernel (issue
+    // slots and the ALU pipe are), and the larger table costs more than the conflicts it removes: one copy is the default.
+    // SEA_B200_VBR_RS=n replicates 2^n times where that fits, for tuning runs.
+    const size_t rings = (size_t)VCfg<2>::kWarps * VCfg<2>::kWarpBytes, room = 220u * 1024u - rings;
+    int rs = 0;
+    if (const char *env = getenv("SEA_B200_VBR_RS")) {
+        rs = atoi(env);
+        if (rs < 0) rs = 0;
+        if (rs > 5) rs = 5;
+        while (rs > 0 && ((lut_bytes / 2u) << rs) > room) rs--;
+    }
+#define SEA_VBR(CC)                                                                                          \
+    switch (rs) {                                                                                            \
+        case 5: return launch_vbr<CC, 5>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
+        case 4: return launch_vbr<CC, 4>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
+        case 3: return launch_vbr<CC, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
+        case 2: return launch_vbr<CC, 2>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
+        case 1: return launch_vbr<CC, 1>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
+        default: return launch_vbr<CC, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+    }
+    if (p.channels == 1) SEA_VBR(1)
+    SEA_VBR(2)
+#undef SEA_VBR
 }
 
 }  // namespace sea

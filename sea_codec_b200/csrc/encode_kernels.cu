@@ -264,6 +264,8 @@ struct FastLut {
 #endif
 };
 
+constexpr uint32_t kCodePitch = 36;  // bytes between the frame rows of a warp's code buffer (search_pass_fast)
+
 template <int FB>
 __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParams &p, const int16_t *__restrict__ x0, uint32_t frames,
                                  const int32_t *__restrict__ tab, int32_t *st_w, int32_t *st_h, int32_t *st_prev, uint8_t *codes,
@@ -381,7 +383,9 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
             unsigned long long rank = 0;
             const int16_t *xs = xbuf + (split ? 0u : grp * F);
-            uint8_t *cbuf = codes + warp * (F * 32u) + lane;  // [frame][lane] per warp: constant stride, immediate offsets when unrolled
+            // [frame][lane] per warp, rows 36 bytes apart (9 words: the column read of the winners' codes below is conflict free);
+            // constant stride, immediate offsets when unrolled
+            uint8_t *cbuf = codes + warp * (F * kCodePitch) + lane;
             // the candidate trial (encoder_base.rs:64-89); NARROW picks the short exact form of the weights penalty
             bool direct_now = kDirect;
             if (FB == 0) {
@@ -467,7 +471,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     for (int i = 0; i < 4; i++) w[i] += delta * sg[i];
                     h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = y;
                     sg[0] = sg[1]; sg[1] = sg[2]; sg[2] = sg[3]; sg[3] = (v >> 31) | 1;  // the clamp keeps the sign
-                    cbuf[f * 32u] = (uint8_t)code;
+                    cbuf[f * kCodePitch] = (uint8_t)code;
                 };
                 if (kUnrolled && FB > 0) {  // the default block: fully unrolled (immediate offsets, no loop control, penalties of one
                                             // step scheduled into the table-load shadow of the next)
@@ -549,7 +553,13 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             // REDUX min-reductions -- high word, low word, order -- need a third of the instructions but measured 5 % slower at
             // 1024 streams: their latency sits on the per-block critical path of a latency-bound kernel.)
             uint32_t g_lane;
-            if (!__any_sync(0xffffffffu, (rank >> 60) != 0ull)) {
+            if (!__any_sync(0xffffffffu, (rank >> 27) != 0ull)) {
+                // ordinary audio: every rank of the block is below 2^27, (rank, ord) fits 31 bits and ONE redux.sync per chain group
+                // finds the minimum (the 64-bit butterfly below is four dependent shuffle rounds, ~8 % of a latency-bound block)
+                const uint32_t key = ((uint32_t)rank << 4) | ord;
+                const uint32_t best = __reduce_min_sync(0xffffu << (grp * 16u), key);
+                g_lane = grp * 16u + ((best + prev) & (nsf - 1u));
+            } else if (!__any_sync(0xffffffffu, (rank >> 60) != 0ull)) {
                 // the usual case: (rank, ord) fits one 64-bit key, a butterfly of 64-bit minima finds the winner's order and
                 // the lane follows from it: sf = (ord + prev) mod 16 (encoder_base.rs:116-117)
                 unsigned long long key = (rank << 4) | ord;
@@ -584,22 +594,37 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 if (mode == 1) vs.keys[blk * C + c] = rank;
                 else put_bits(chunk_buf, sf_sec_bit + (blk * C + c) * s, s, sf);
             }
-            if (mode != 1 && active) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
-                uint32_t blockbit, rowbits, prefix;
+            if (mode != 1) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
+                // One lane per FRAME: the codes of the warp's two channels are adjacent bits of the frame's row, so lane f reads both
+                // winners' codes and writes them as one field (it was one lane per code: two divergent rounds of put_bits per
+                // block -- 14 % of the stall samples of profiles/r02_enc_cbr3_128_*).
+                const uint32_t g0 = __shfl_sync(0xffffffffu, g_lane, 0), g1 = __shfl_sync(0xffffffffu, g_lane, 16);
+                const bool two = !split && cb + 1u < C;  // group 1 carries a real channel
+                uint32_t blockbit, rowbits, prefix0, size0, size1;
                 if (mode == 2) {
                     if (vs.blkbit_sh) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(blockbit) : "r"(vs.blkbit_sh + blk * 4u));
                     else blockbit = vs.blkbit[blk];
-                    rowbits = bdesc >> 12;
-                    prefix = (bdesc >> 4) & 255u;
+                    const uint32_t d0 = __shfl_sync(0xffffffffu, bdesc, 0), d1 = __shfl_sync(0xffffffffu, bdesc, 16);
+                    rowbits = d0 >> 12;
+                    prefix0 = (d0 >> 4) & 255u;
+                    size0 = d0 & 15u;
+                    size1 = d1 & 15u;
                 } else {
                     rowbits = C * size;
                     blockbit = blk * F * rowbits;
-                    prefix = c * size;
+                    prefix0 = cb * size;
+                    size0 = size1 = size;
                 }
-                const uint8_t *wbuf = codes + warp * (F * 32u) + g_lane;
-                __syncwarp(__activemask());  // the winner's codes were written by another lane
-                for (uint32_t f = sf; f < nf; f += lpc)
-                    put_bits(chunk_buf, res_sec_bit + blockbit + f * rowbits + prefix, size, wbuf[f * 32u]);
+                __syncwarp();  // the winners' codes were written by other lanes
+                if (lane < nf) {
+                    const uint8_t *row = codes + warp * (F * kCodePitch) + lane * kCodePitch;
+                    uint32_t field = row[g0], n = size0;
+                    if (two) {
+                        field = (field << size1) | row[g1];
+                        n += size1;
+                    }
+                    put_bits(chunk_buf, res_sec_bit + blockbit + lane * rowbits + prefix0, n, field);
+                }
             }
             __syncwarp();  // everybody is done with this block's samples and codes
             if (pre) {

@@ -59,6 +59,24 @@ bool decode_mc_supported(const DecFastParams &p);
 cudaError_t launch_decode_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
                              int *d_err, cudaStream_t stream);
 
+// Warps per CTA for the lane-per-chunk kernels (one full-width CTA per SM is their design point).  A grid of only a few waves
+// of such CTAs ends with most SMs idle while the last wave drains (BASELINE config 3 shape: 2.5 waves -> 16 % lost), so short
+// grids are cut into narrower CTAs -- the same warps per SM, several CTAs resident -- until the tail is a small share.
+inline uint32_t pick_cta_warps(uint64_t total_chunks, uint32_t chunks_per_warp, uint32_t max_warps)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t warps = max_warps;
+    while (warps > 4u && warps % 2u == 0u) {
+        const uint64_t per_cta = (uint64_t)warps * chunks_per_warp;
+        const uint64_t ctas = (total_chunks + per_cta - 1) / per_cta;
+        if (ctas >= (uint64_t)sms * (max_warps / warps) * 12u) break;  // >= 12 waves: the tail is under ~4 %
+        warps /= 2u;
+    }
+    return warps;
+}
+
 // ---- encode ------------------------------------------------------------------------------------------------
 struct EncStream {
     uint64_t pcm_off;   // sample offset of the stream's PCM

@@ -21,7 +21,7 @@ elif os.environ.get("PROBE_STREAM") == "torch":
 frames = int(sys.argv[6]) if len(sys.argv) > 6 else secs * 44100  # argv[6]: exact frame count (e.g. a multiple of 5120: no partial chunk)
 vbr = bool(int(os.environ.get("PROBE_VBR", "0")))
 st = S.EncoderSettings(residual_bits=bits, vbr=vbr)
-u = min(n, 16)
+u = next(k for k in range(min(n, 16), 0, -1) if n % k == 0)
 pcm = synth.gen_batch_torch(u, frames, ch, 44100, dev)
 bound = ctx.encode_bound(frames, ch, st)
 stride = (bound + 15) // 16 * 16

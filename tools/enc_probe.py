@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 ctx = S.Context(0)
 frames = secs * 44100
 st = S.EncoderSettings(residual_bits=bits, vbr=vbr)
-u = min(n, 16)
+u = next(k for k in range(min(n, 16), 0, -1) if n % k == 0)
 pcm = synth.gen_batch_torch(u, frames, ch, 44100, dev).repeat(n // u, 1).contiguous()
 bound = ctx.encode_bound(frames, ch, st)
 stride = (bound + 15) // 16 * 16
