@@ -592,13 +592,31 @@ def main():
                "sample": f"all {n} streams per step as {calls} calls of {ne} streams over the same pinned buffers; PCIe-bound"}
         # ---- e2e encode: sea_b200_encode_batch, host PCM in (2 B/sample), .sea out; a step = ns streams as ns / ne_e calls
         if not args.skip_encode:
+            # all ns streams in one call when the host has the memory for their pinned PCM (the kernel wants every stream in
+            # flight; the library pipelines slices of time, capi.cu encode_batch_sliced), else calls of ne streams
             ne_e = min(ne, ns)
+            try:
+                import psutil
+
+                if ns * spp * 2 * 2 * W < psutil.virtual_memory().available // 2:
+                    ne_e = ns
+            except Exception:
+                pass
             while ns % ne_e:
                 ne_e -= 1
+            if ne_e > ne:
+                try:
+                    del h_pcm
+                    h_pcm = torch.empty(ne_e * spp, dtype=torch.int16).pin_memory()
+                    h_sea = torch.empty(ne_e * stride, dtype=torch.uint8).pin_memory()
+                except RuntimeError:
+                    ne_e = ne
+                    h_pcm = torch.empty(ne_e * spp, dtype=torch.int16).pin_memory()
             calls_e = ns // ne_e
             h_pcm[: ne_e * spp].copy_(b.pcm[: ne_e * spp])
             torch.cuda.synchronize()
             out_off_e = np.arange(ne_e, dtype=np.uint64) * stride
+            pcm_off_e = np.arange(ne_e, dtype=np.uint64) * spp
 
             def enc_e2e_step():
                 for _ in range(calls_e):

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -65,6 +66,11 @@ struct sea_b200_ctx {
         DevBuf in, out, table;
         int *d_err = nullptr;
     } aux;
+    // time-sliced host-buffer encode (sea_b200_encode_batch): upload / kernel / download of neighbouring slices overlap
+    struct {
+        cudaEvent_t up[2] = {}, kern[2] = {}, down[2] = {};
+        DevBuf in[2], out[2], state;
+    } pipe;
     std::string last_error;
     uint64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -372,6 +378,28 @@ int plan_encode(sea_b200_ctx *ctx, uint32_t n_streams, const uint64_t *pcm_offse
     return SEA_B200_OK;
 }
 
+// One encode launch on the context's stream, nothing waited for: `slot` selects which n-entry region of the descriptor / length /
+// first-chunk arrays the launch uses (the time-sliced batch encode keeps one per slice and reads them all back at the end).
+// The error word and the tie counters are NOT reset here: they accumulate over the launches of one call.
+int enqueue_encode(sea_b200_ctx *ctx, EncodeJob &job, const int16_t *d_pcm, uint8_t *d_out, int32_t *d_state, uint32_t slot,
+                   bool descriptors_uploaded)
+{
+    const uint32_t n = job.params.n_streams;
+    EncWorkspace ws = {};
+    ws.vbr_scratch_stride = enc_vbr_scratch_bytes(job.params);
+    if (ws.vbr_scratch_stride) {
+        CU(ctx->scratch.reserve(ws.vbr_scratch_stride * n));
+        ws.vbr_scratch = ctx->scratch.as<uint8_t>();
+    }
+    EncStream *d_streams = ctx->streams.as<EncStream>() + (size_t)slot * n;
+    if (!descriptors_uploaded)
+        CU(cudaMemcpyAsync(d_streams, job.streams.data(), sizeof(EncStream) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_encode_generic(d_pcm, d_out, d_streams, job.params, ctx->tabs, d_state, ctx->lens.as<uint64_t>() + (size_t)slot * n,
+                             ctx->chunk0.as<uint32_t>() + (size_t)slot * n, ctx->ties.as<unsigned long long>(), ws, ctx->d_err, ctx->stream));
+    ctx->launches++;
+    return SEA_B200_OK;
+}
+
 int run_encode(sea_b200_ctx *ctx, EncodeJob &job, const int16_t *d_pcm, uint8_t *d_out, int32_t *d_state, uint64_t *h_out_lens,
                uint32_t *h_chunk0)
 {
@@ -436,6 +464,168 @@ uint64_t encode_bound_bytes(const EncodePlan &pl, uint64_t n_frames)
         bytes += 4 + 16ull * pl.channels + (items * pl.s + 7) / 8 + (pl.vbr ? (items * 2 + 7) / 8 : 0) + (rem * pl.channels * bits + 7) / 8;
     }
     return bytes;
+}
+
+// ---- time-sliced host-buffer encode --------------------------------------------------------------------------------------------
+// An encoder stream is serial (LMS + prev_scalefactor carry over, encoder_base.rs:181-182), so a batch cannot be pipelined by
+// stream groups without starving the kernel of parallel streams.  It is cut in TIME instead: a slice = `K` chunks of every stream;
+// slice j+1 is uploaded while slice j is encoded (the per-stream state stays on the device between the launches, exactly like a
+// streaming handle's make_chunks) and slice j-1 is downloaded.  Returns 1 when slicing does not apply (short or tiny batches).
+int encode_batch_sliced(sea_b200_ctx *ctx, uint32_t n, const int16_t *pcm, const uint64_t *pcm_offsets, const uint32_t *n_frames,
+                        uint32_t sample_rate, uint32_t channels, const sea_b200_settings *settings, const EncodePlan &pl, uint8_t *out,
+                        const uint64_t *out_offsets, uint64_t *out_lens)
+{
+    uint64_t forced = 0;  // SEA_B200_ENC_SLICE: 0 = never slice, k > 0 = slices of k chunks whatever the batch size (tests, tuning)
+    if (const char *env = getenv("SEA_B200_ENC_SLICE")) {
+        if (env[0] == '0') return 1;
+        forced = (uint64_t)atoll(env);
+    }
+    uint64_t max_frames = 0, total_samples = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        max_frames = std::max<uint64_t>(max_frames, n_frames[i]);
+        total_samples += (uint64_t)n_frames[i] * channels;
+    }
+    if (!forced && total_samples < (32ull << 20)) return 1;
+    const uint64_t chunk_samples = (uint64_t)pl.N * channels;
+    uint64_t K = (512ull << 20) / std::max<uint64_t>(1, (uint64_t)n * chunk_samples);  // ~1 GB of PCM per slice
+    K = forced ? forced : std::min<uint64_t>(std::max<uint64_t>(K, 4), 1024);
+    const uint64_t slice_frames = K * pl.N, S = (max_frames + slice_frames - 1) / slice_frames;
+    if (S < (forced ? 2u : 3u)) return 1;
+    const uint64_t slice_samples = slice_frames * channels, out_region = K * (uint64_t)pl.max_chunk_bytes;
+
+    // regular layouts (equal lengths, equal strides) move a slice with one 2-D copy each way
+    bool regular = n > 1;
+    const uint64_t pstride = n > 1 ? pcm_offsets[1] - pcm_offsets[0] : 0, ostride = n > 1 ? out_offsets[1] - out_offsets[0] : 0;
+    for (uint32_t i = 1; i < n && regular; i++)
+        regular = n_frames[i] == n_frames[0] && pcm_offsets[i] == pcm_offsets[0] + i * pstride && out_offsets[i] == out_offsets[0] + i * ostride &&
+                  pcm_offsets[1] > pcm_offsets[0] && out_offsets[1] > out_offsets[0];
+    if (regular && (pstride < (uint64_t)n_frames[0] * channels || ostride < encode_bound_bytes(pl, n_frames[0]))) regular = false;
+
+    cudaStream_t comp = ctx->stream, up = ctx->aux.stream, down = ctx->aux.side;
+    for (int b = 0; b < 2; b++) {
+        if (!ctx->pipe.up[b]) CU(cudaEventCreateWithFlags(&ctx->pipe.up[b], cudaEventDisableTiming));
+        if (!ctx->pipe.kern[b]) CU(cudaEventCreateWithFlags(&ctx->pipe.kern[b], cudaEventDisableTiming));
+        if (!ctx->pipe.down[b]) CU(cudaEventCreateWithFlags(&ctx->pipe.down[b], cudaEventDisableTiming));
+        CU(ctx->pipe.in[b].reserve((uint64_t)n * slice_samples * 2 + 64));
+        CU(ctx->pipe.out[b].reserve((uint64_t)n * out_region + 64));
+    }
+    CU(ctx->streams.reserve(sizeof(EncStream) * n * S));
+    CU(ctx->lens.reserve(sizeof(uint64_t) * n * S));
+    CU(ctx->chunk0.reserve(sizeof(uint32_t) * n * S));
+    CU(ctx->ties.reserve(sizeof(unsigned long long) * ((size_t)n + 1u)));
+    {   // EncoderBase::new for every stream (encoder_base.rs:29-41, lms.rs:19-32)
+        std::vector<int32_t> init((size_t)n * channels * kEncStateWords, 0);
+        for (size_t c = 0; c < (size_t)n * channels; c++) {
+            init[c * kEncStateWords + 4 + 2] = -(1 << 13);
+            init[c * kEncStateWords + 4 + 3] = 1 << 14;
+        }
+        CU(ctx->pipe.state.reserve(init.size() * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(ctx->pipe.state.p, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice, comp));
+    }
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), comp));
+    CU(cudaMemsetAsync(ctx->ties.p, 0, sizeof(unsigned long long) * ((size_t)n + 1u), comp));
+    ctx->h_ties.assign((size_t)n + 1u, 0ull);
+    // every slice's launch descriptors, planned and uploaded up front (a pageable upload inside the loop would make the host
+    // wait for the previous kernel before it could queue the next copies)
+    std::vector<EncodeJob> jobs(S);
+    std::vector<uint32_t> all_frames((size_t)S * n);
+    {
+        std::vector<uint64_t> o_pcm(n), o_out(n);
+        std::vector<EncStream> all((size_t)S * n);
+        for (uint32_t i = 0; i < n; i++) {
+            o_pcm[i] = (uint64_t)i * slice_samples;
+            o_out[i] = (uint64_t)i * out_region;
+        }
+        for (uint64_t j = 0; j < S; j++) {
+            uint32_t *fr = all_frames.data() + (size_t)j * n;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint64_t done = std::min<uint64_t>(n_frames[i], j * slice_frames);
+                fr[i] = (uint32_t)std::min<uint64_t>(slice_frames, n_frames[i] - done);
+            }
+            int prc = plan_encode(ctx, n, o_pcm.data(), fr, sample_rate, channels, settings, o_out.data(), true, &jobs[j]);
+            if (prc) return prc;
+            std::copy(jobs[j].streams.begin(), jobs[j].streams.end(), all.begin() + (size_t)j * n);
+        }
+        CU(cudaMemcpyAsync(ctx->streams.p, all.data(), sizeof(EncStream) * all.size(), cudaMemcpyHostToDevice, comp));
+    }
+    CU(cudaEventRecord(ctx->ev0, comp));
+    CU(cudaEventRecord(ctx->pipe.kern[0], comp));  // orders the side streams behind whatever the caller queued on the context's stream
+    CU(cudaStreamWaitEvent(up, ctx->pipe.kern[0], 0));
+    CU(cudaStreamWaitEvent(down, ctx->pipe.kern[0], 0));
+
+    std::vector<uint64_t> lens_j(n);
+    for (uint32_t i = 0; i < n; i++) out_lens[i] = kFileHeaderBytes;
+    int rc = SEA_B200_OK;
+    for (uint64_t j = 0; j < S && rc == SEA_B200_OK; j++) {
+        const int b = (int)(j & 1);
+        bool vbr_tail = false;
+        const uint32_t *s_frames = all_frames.data() + (size_t)j * n;
+        for (uint32_t i = 0; i < n; i++)
+            if (pl.vbr && s_frames[i] % pl.N) vbr_tail = true;
+        // ---- upload (waits until the kernel that last read this buffer is done)
+        if (j >= 2) CU(cudaStreamWaitEvent(up, ctx->pipe.kern[b], 0));
+        int16_t *d_in = ctx->pipe.in[b].as<int16_t>();
+        if (regular && s_frames[0]) {
+            CU(cudaMemcpy2DAsync(d_in, slice_samples * 2, pcm + pcm_offsets[0] + j * slice_samples, pstride * 2, (size_t)s_frames[0] * channels * 2, n,
+                                 cudaMemcpyHostToDevice, up));
+        } else if (!regular) {
+            for (uint32_t i = 0; i < n; i++)
+                if (s_frames[i])
+                    CU(cudaMemcpyAsync(d_in + (uint64_t)i * slice_samples, pcm + pcm_offsets[i] + j * slice_samples,
+                                       (size_t)s_frames[i] * channels * 2, cudaMemcpyHostToDevice, up));
+        }
+        CU(cudaEventRecord(ctx->pipe.up[b], up));
+        // ---- kernel (waits for the upload, and for the download that last read this output buffer)
+        CU(cudaStreamWaitEvent(comp, ctx->pipe.up[b], 0));
+        if (j >= 2) CU(cudaStreamWaitEvent(comp, ctx->pipe.down[b], 0));
+        rc = enqueue_encode(ctx, jobs[j], d_in, ctx->pipe.out[b].as<uint8_t>(), ctx->pipe.state.as<int32_t>(), (uint32_t)j, true);
+        if (rc) break;
+        CU(cudaEventRecord(ctx->pipe.kern[b], comp));
+        // ---- lengths of this slice's output per stream.  Full chunks have the plan's size (CBR and VBR alike, encoder_vbr.rs:66-96
+        // gives constant bucket counts); a CBR partial chunk follows from the frame count; a VBR partial chunk has to be read back.
+        if (vbr_tail) {
+            CU(cudaMemcpyAsync(lens_j.data(), ctx->lens.as<uint64_t>() + (size_t)j * n, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, comp));
+            CU(cudaStreamSynchronize(comp));
+        } else {
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t full = s_frames[i] / pl.N, rem = s_frames[i] % pl.N;
+                lens_j[i] = (uint64_t)full * pl.full_chunk_bytes + (rem ? cbr_chunk_bytes(rem, channels, pl.s, pl.F, pl.hdr_bits) : 0u);
+            }
+        }
+        // ---- download into the ranges the streams own
+        CU(cudaStreamWaitEvent(down, ctx->pipe.kern[b], 0));
+        const uint8_t *d_o = ctx->pipe.out[b].as<uint8_t>();
+        const uint64_t file_off = kFileHeaderBytes + j * K * (uint64_t)pl.full_chunk_bytes;
+        bool same_len = regular;
+        for (uint32_t i = 1; i < n && same_len; i++) same_len = lens_j[i] == lens_j[0];
+        if (same_len && lens_j[0]) {
+            CU(cudaMemcpy2DAsync(out + out_offsets[0] + file_off, ostride, d_o, out_region, lens_j[0], n, cudaMemcpyDeviceToHost, down));
+        } else if (!same_len) {
+            for (uint32_t i = 0; i < n; i++)
+                if (lens_j[i]) CU(cudaMemcpyAsync(out + out_offsets[i] + file_off, d_o + (uint64_t)i * out_region, lens_j[i], cudaMemcpyDeviceToHost, down));
+        }
+        CU(cudaEventRecord(ctx->pipe.down[b], down));
+        for (uint32_t i = 0; i < n; i++) out_lens[i] += lens_j[i];
+    }
+    CU(cudaEventRecord(ctx->ev1, comp));
+    int dev_err = 0;
+    CU(cudaMemcpyAsync(&dev_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, comp));
+    if (pl.vbr) CU(cudaMemcpyAsync(ctx->h_ties.data(), ctx->ties.p, sizeof(unsigned long long) * ((size_t)n + 1u), cudaMemcpyDeviceToHost, comp));
+    CU(cudaStreamSynchronize(comp));
+    CU(cudaStreamSynchronize(up));
+    CU(cudaStreamSynchronize(down));
+    if (rc) return rc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;  // first launch to last, uploads the kernels waited for included
+    ctx->last_ties = ctx->h_ties[0];
+    if ((rc = map_dev_error(ctx, dev_err)) != SEA_B200_OK) return rc;
+    // file headers (file.rs:78-93): chunk_size = the first chunk's size (file.rs:166-168, `as u16`), written by the host
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t first = n_frames[i] >= pl.N ? pl.full_chunk_bytes : out_lens[i] - kFileHeaderBytes;
+        write_file_header(out + out_offsets[i], (uint8_t)channels, (uint16_t)first, (uint16_t)pl.N, sample_rate, n_frames[i]);
+    }
+    return SEA_B200_OK;
 }
 
 }  // namespace
@@ -531,6 +721,14 @@ void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
     ctx->misc.release();
     if (ctx->d_err) cudaFree(ctx->d_err);
     ctx->ties.release();
+    for (int i = 0; i < 2; i++) {
+        if (ctx->pipe.up[i]) cudaEventDestroy(ctx->pipe.up[i]);
+        if (ctx->pipe.kern[i]) cudaEventDestroy(ctx->pipe.kern[i]);
+        if (ctx->pipe.down[i]) cudaEventDestroy(ctx->pipe.down[i]);
+        ctx->pipe.in[i].release();
+        ctx->pipe.out[i].release();
+    }
+    ctx->pipe.state.release();
     if (ctx->aux.stream) { cudaStreamSynchronize(ctx->aux.stream); cudaStreamDestroy(ctx->aux.stream); }
     if (ctx->aux.side) { cudaStreamSynchronize(ctx->aux.side); cudaStreamDestroy(ctx->aux.side); }
     if (ctx->aux.ev_fork) cudaEventDestroy(ctx->aux.ev_fork);
@@ -869,6 +1067,10 @@ int sea_b200_encode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const int16_t *
     }
     if (hi == 0) lo = 0;
     if (hi && !pcm) return SEA_B200_ERR_INVALID_PARAMETERS;
+    if (hi) {  // long batches: slices of time pipelined over the copy engines (same bytes; see encode_batch_sliced)
+        rc = encode_batch_sliced(ctx, n_streams, pcm, pcm_offsets, n_frames, sample_rate, channels, settings, job.plan, out, out_offsets, out_lens);
+        if (rc <= 0) return rc;
+    }
     for (auto &e : job.streams) {
         e.pcm_off -= (e.n_frames ? lo : e.pcm_off);
         e.out_off -= olo;

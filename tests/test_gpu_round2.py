@@ -284,3 +284,49 @@ def test_device_synth_matches_the_host_recipe(ctx):
     ctx.synth_pcm_device(mono.data_ptr(), 1000, np.array([7, 8, 9]), 1000, 1, 48000)
     for i, k in enumerate((7, 8, 9)):
         assert np.array_equal(mono.cpu().numpy().reshape(3, 1000)[i], synth.gen_stream(k, 1000, 1, 48000))
+
+
+# ------------------------------------------------------------------------------------------------ time-sliced host-buffer encode
+
+@pytest.fixture
+def force_slices():
+    old = os.environ.get("SEA_B200_ENC_SLICE")
+    yield lambda v: os.environ.__setitem__("SEA_B200_ENC_SLICE", v)
+    if old is None:
+        os.environ.pop("SEA_B200_ENC_SLICE", None)
+    else:
+        os.environ["SEA_B200_ENC_SLICE"] = old
+
+
+@pytest.mark.parametrize("kw", [dict(residual_bits=3.0), dict(residual_bits=3.0, vbr=True), dict(residual_bits=5.0, scale_factor_bits=5)])
+def test_time_sliced_batch_encode_equals_one_shot(ctx, oracle, kw, force_slices):
+    """sea_b200_encode_batch cuts long batches into slices of k chunks (upload / kernel / download pipelined, LMS state kept on the
+    device between the launches).  Forced here to 2- and 3-chunk slices on a ragged batch: every stream -- full slices, a stream
+    that ends early, partial last chunks (CBR: size known on the host; VBR: read back), an empty stream -- must equal the
+    oracle's one-shot bytes, in a packed (2-D copies) and in a scattered layout, and nothing outside the owned ranges may change."""
+    ch = 2
+    lens = [5120 * 7 + 333, 5120 * 7 + 333, 5120 * 3, 5120 * 2 + 17, 0, 5120 * 9 + 4000]
+    streams = [synth.gen_stream(600 + i, n, ch, 44100) for i, n in enumerate(lens)]
+    st, ost = _settings_pair(oracle, **kw)
+    refs = [oracle.sea_encode(x, 44100, ch, ost) for x in streams]
+    for k in ("2", "3"):
+        force_slices(k)
+        assert ctx.encode_batch(streams, 44100, ch, st) == refs, f"{k}-chunk slices, ragged batch"
+    # regular layout: equal lengths at a constant stride (the 2-D copy route), with gaps that must stay untouched
+    force_slices("2")
+    n, frames, gap = 5, 5120 * 5 + 1000, 500
+    same = [synth.gen_stream(620 + i, frames, ch, 44100) for i in range(n)]
+    want = [oracle.sea_encode(x, 44100, ch, ost) for x in same]
+    spp, bound = frames * ch, ctx.encode_bound(frames, ch, st)
+    pcm = np.zeros(n * (spp + gap), dtype=np.int16)
+    for i, x in enumerate(same):
+        pcm[i * (spp + gap): i * (spp + gap) + spp] = x
+    out = np.full(n * (bound + gap) + gap, 0xA5, dtype=np.uint8)
+    out_off = gap + np.arange(n, dtype=np.uint64) * (bound + gap)
+    got = ctx.encode_batch_host(pcm.ctypes.data, np.arange(n) * (spp + gap), np.full(n, frames), 44100, ch, st, out.ctypes.data, out_off)
+    owned = np.zeros(out.size, dtype=bool)
+    for i in range(n):
+        o = int(out_off[i])
+        assert out[o: o + int(got[i])].tobytes() == want[i], i
+        owned[o: o + int(got[i])] = True
+    assert np.all(out[~owned] == 0xA5)
