@@ -145,6 +145,28 @@ int sea_b200_decode_batch_device(sea_b200_ctx *ctx, uint32_t n_streams, const ui
                                  const uint64_t *sea_lens, const uint8_t *headers, int16_t *d_pcm,
                                  const uint64_t *pcm_offsets, const uint64_t *pcm_caps, uint64_t *n_samples);
 
+/* ---------------------------------------------------------------- batch across the GPUs of one box (in-process) */
+
+/* BASELINE north star / SURVEY 8e: streams are partitioned across the GPUs, nothing is exchanged between them, only per-GPU
+ * counts are gathered on the host.  A sea_b200_multi owns one context per listed device; a call shards the batch into one
+ * contiguous range of streams per GPU (balanced by PCM samples resp. .sea bytes), runs the single-GPU host-buffer call above
+ * on every range from one host thread per GPU, and reports where each GPU's range starts and how much it produced.
+ * devices == NULL means devices 0 .. n_devices-1.  The arrays first_stream_of_device / *_per_device have n_devices entries
+ * and may be NULL.  Results are identical to the single-GPU call on the same arguments. */
+typedef struct sea_b200_multi sea_b200_multi;
+int sea_b200_multi_create(const int *devices, uint32_t n_devices, sea_b200_multi **multi);
+void sea_b200_multi_destroy(sea_b200_multi *multi);
+uint32_t sea_b200_multi_device_count(const sea_b200_multi *multi);
+sea_b200_ctx *sea_b200_multi_ctx(const sea_b200_multi *multi, uint32_t index); /* the index-th GPU's context (owned by multi) */
+const char *sea_b200_multi_last_error(const sea_b200_multi *multi);
+int sea_b200_multi_encode_batch(sea_b200_multi *multi, uint32_t n_streams, const int16_t *pcm, const uint64_t *pcm_offsets,
+                                const uint32_t *n_frames, uint32_t sample_rate, uint32_t channels,
+                                const sea_b200_settings *settings, uint8_t *out, const uint64_t *out_offsets, uint64_t *out_lens,
+                                uint32_t *first_stream_of_device, uint64_t *bytes_per_device);
+int sea_b200_multi_decode_batch(sea_b200_multi *multi, uint32_t n_streams, const uint8_t *sea, const uint64_t *sea_offsets,
+                                const uint64_t *sea_lens, int16_t *pcm, const uint64_t *pcm_offsets, const uint64_t *pcm_caps,
+                                uint64_t *n_samples, uint32_t *first_stream_of_device, uint64_t *samples_per_device);
+
 /* ---------------------------------------------------------------- streaming seam (one chunk per call) */
 
 /* SeaFile::new + EncoderBase::new (file.rs:111-129, encoder_base.rs:29-41): per-channel LMS state and

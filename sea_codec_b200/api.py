@@ -145,6 +145,15 @@ SYMBOLS = {
     "sea_b200_int32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sea_b200_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "sea_b200_last_vbr_ties": (C.c_uint64, [C.c_void_p]),
+    "sea_b200_multi_create": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "sea_b200_multi_destroy": (None, [C.c_void_p]),
+    "sea_b200_multi_device_count": (C.c_uint32, [C.c_void_p]),
+    "sea_b200_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "sea_b200_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "sea_b200_multi_encode_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                              C.POINTER(_Settings), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sea_b200_multi_decode_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sea_b200_last_vbr_ties_per_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "sea_b200_synth_pcm_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]),
@@ -388,6 +397,61 @@ class Context:
                                                          hd.ctypes.data, C.c_void_p(d_pcm), po.ctypes.data,
                                                          caps.ctypes.data if caps is not None else None, n.ctypes.data))
         return n
+
+
+class MultiContext:
+    """One context per GPU of the box (sea_b200_multi): batch calls shard the streams over the GPUs in-process, one host thread
+    per GPU, nothing exchanged between them; per-GPU counts come back with the result."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._L = lib()
+        self._h = C.c_void_p()
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._L.sea_b200_multi_create(devs.ctypes.data, devs.size, C.byref(self._h))
+        if rc:
+            raise SeaError(rc, "sea_b200_multi_create failed (no CPU fallback)")
+        self.devices = list(int(d) for d in devs)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.sea_b200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise SeaError(rc, self._L.sea_b200_multi_last_error(self._h).decode(errors="replace"))
+
+    def encode_batch_host(self, pcm_ptr: int, pcm_offsets, n_frames, sample_rate: int, channels: int, settings: EncoderSettings,
+                          out_ptr: int, out_offsets):
+        """-> (out_lens[n], first_stream_of_device[g], bytes_per_device[g])"""
+        po, oo = _u64(pcm_offsets), _u64(out_offsets)
+        nf = np.ascontiguousarray(n_frames, dtype=np.uint32)
+        lens = np.zeros(nf.size, dtype=np.uint64)
+        first = np.zeros(len(self.devices), dtype=np.uint32)
+        per = np.zeros(len(self.devices), dtype=np.uint64)
+        st = settings._c()
+        self._check(self._L.sea_b200_multi_encode_batch(self._h, nf.size, C.c_void_p(pcm_ptr), po.ctypes.data, nf.ctypes.data, sample_rate,
+                                                        channels, C.byref(st), C.c_void_p(out_ptr), oo.ctypes.data, lens.ctypes.data,
+                                                        first.ctypes.data, per.ctypes.data))
+        return lens, first, per
+
+    def decode_batch_host(self, sea_ptr: int, sea_offsets, sea_lens, pcm_ptr: int, pcm_offsets, pcm_caps=None):
+        """-> (n_samples[n], first_stream_of_device[g], samples_per_device[g])"""
+        so, sl, po = _u64(sea_offsets), _u64(sea_lens), _u64(pcm_offsets)
+        caps = _u64(pcm_caps) if pcm_caps is not None else None
+        n = np.zeros(so.size, dtype=np.uint64)
+        first = np.zeros(len(self.devices), dtype=np.uint32)
+        per = np.zeros(len(self.devices), dtype=np.uint64)
+        self._check(self._L.sea_b200_multi_decode_batch(self._h, so.size, C.c_void_p(sea_ptr), so.ctypes.data, sl.ctypes.data,
+                                                        C.c_void_p(pcm_ptr), po.ctypes.data, caps.ctypes.data if caps is not None else None,
+                                                        n.ctypes.data, first.ctypes.data, per.ctypes.data))
+        return n, first, per
 
 
 _default_ctx: Optional[Context] = None

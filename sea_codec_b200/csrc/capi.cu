@@ -1268,12 +1268,16 @@ int sea_b200_decoder_decode_chunk(sea_b200_decoder *dec, const uint8_t *chunk, u
     d.channels = h.channels;
     job.total_chains = h.channels;
     job.first = h;
-    job.uniform = false;  // one chunk: the generic kernel is the latency path
+    // One chunk is a serial chain per channel -- latency, not throughput.  The host already holds the chunk's header word, so
+    // mono / stereo chunks go to the staged kernel (residuals through shared memory: ~3x shorter chain steps than the generic
+    // kernel's global-memory bit reads); run_decode falls back to the generic kernel for anything it does not cover.
+    job.uniform = true;
+    const uint32_t hdr_word = (uint32_t)chunk[0] | ((uint32_t)chunk[1] << 8) | ((uint32_t)chunk[2] << 16) | ((uint32_t)chunk[3] << 24);
     CU(ctx->in.reserve(len + 64));
     CU(ctx->out.reserve(frames * h.channels * 2 + 64));
     CU(cudaMemcpyAsync(ctx->in.p, chunk, len, cudaMemcpyHostToDevice, ctx->stream));
     DecLane L = decode_lane(ctx, 0);
-    int rc = run_decode(ctx, L, job, ctx->in.as<uint8_t>(), len, ctx->out.as<int16_t>(), false, 0);
+    int rc = run_decode(ctx, L, job, ctx->in.as<uint8_t>(), len, ctx->out.as<int16_t>(), true, hdr_word);
     if (rc) return rc;
     CU(cudaMemcpyAsync(pcm, ctx->out.p, frames * h.channels * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

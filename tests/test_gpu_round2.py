@@ -330,3 +330,50 @@ def test_time_sliced_batch_encode_equals_one_shot(ctx, oracle, kw, force_slices)
         assert out[o: o + int(got[i])].tobytes() == want[i], i
         owned[o: o + int(got[i])] = True
     assert np.all(out[~owned] == 0xA5)
+
+
+# ------------------------------------------------------------------------------------------------ in-process multi-GPU batch API
+
+def _device_sets():
+    import torch
+
+    n = torch.cuda.device_count()
+    sets = [[0], [0, 0], [0, 0, 0]]  # several contexts on one GPU exercise the sharding and the host threads on any box
+    if n >= 2:
+        sets.append(list(range(n)))
+    return sets
+
+
+def test_multi_gpu_batch_calls_equal_the_single_gpu_result(ctx, oracle):
+    """sea_b200_multi_{encode,decode}_batch (shard by stream, one host thread + context per GPU, only per-GPU counts
+    gathered): same bytes / samples as the single-context call and the oracle, whatever the number of devices; the reported
+    ranges tile the batch and the per-device counts add up."""
+    ch = 2
+    lens = [5120 * 3 + 100 * i for i in range(7)] + [17, 5120]  # (an empty stream encodes to a header the reference refuses to decode)
+    streams = [synth.gen_stream(800 + i, n, ch, 44100) for i, n in enumerate(lens)]
+    n = len(streams)
+    for kw in (dict(residual_bits=3.0), dict(residual_bits=4.5, vbr=True)):
+        st, ost = _settings_pair(oracle, **kw)
+        refs = [oracle.sea_encode(x, 44100, ch, ost) for x in streams]
+        want_pcm = [oracle.sea_decode(r).samples for r in refs]
+        pcm_off = np.concatenate([[0], np.cumsum([x.size for x in streams])[:-1]]).astype(np.uint64)
+        flat = np.concatenate(streams)
+        bounds = np.array([ctx.encode_bound(k, ch, st) for k in lens], dtype=np.uint64)
+        out_off = np.concatenate([[0], np.cumsum(bounds + 7)[:-1]]).astype(np.uint64)
+        for devs in _device_sets():
+            m = S.MultiContext(devs)
+            out = np.zeros(int((bounds + 7).sum()), dtype=np.uint8)
+            got_lens, first, per = m.encode_batch_host(flat.ctypes.data, pcm_off, np.array(lens, dtype=np.uint32), 44100, ch, st,
+                                                       out.ctypes.data, out_off)
+            assert first[0] == 0 and np.all(np.diff(first.astype(np.int64)) >= 0) and int(per.sum()) == int(got_lens.sum())
+            for i in range(n):
+                assert out[int(out_off[i]): int(out_off[i]) + int(got_lens[i])].tobytes() == refs[i], (devs, kw, i)
+            # decode what was just encoded, from the same buffer layout
+            pcm = np.zeros(flat.size + 16, dtype=np.int16)
+            ns, first_d, per_d = m.decode_batch_host(out.ctypes.data, out_off, got_lens, pcm.ctypes.data, pcm_off)
+            assert int(per_d.sum()) == int(ns.sum()) == flat.size
+            for i in range(n):
+                assert np.array_equal(pcm[int(pcm_off[i]): int(pcm_off[i]) + int(ns[i])], want_pcm[i]), (devs, kw, i)
+            m.close()
+    with pytest.raises(S.SeaError):
+        S.MultiContext([99])
