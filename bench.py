@@ -639,6 +639,46 @@ def main():
     del pcm_out, view
     torch.cuda.empty_cache()
 
+    # ---- generic-path shapes (the reference's own tests: 3 channels, scale_factor_bits 3 and 5 -- tests/test.rs:35-64): rows that
+    # do not reach the lane-per-chunk kernels, so that the cliff is on record.  1024 unique 20 s streams each, rank 0's GPU only.
+    other = None
+    if not args.skip_encode and info.rank == 0:
+        other = []
+        po = torch.empty(1024 * 20 * RATE * 3, dtype=torch.int16, device=dev)
+        for chs, kw in ((3, dict(residual_bits=3.0)), (2, dict(residual_bits=3.0, scale_factor_bits=3)),
+                        (2, dict(residual_bits=3.0, scale_factor_bits=5)), (2, dict(residual_bits=3.0, scale_factor_bits=5, vbr=True))):
+            fr_o, n_o = 20 * RATE, 1024
+            bo = Batch(torch, dev, n_o, fr_o, chs)
+            ctx.synth_pcm_device(bo.pcm.data_ptr(), bo.spp, (1 << 17) + np.arange(n_o, dtype=np.uint32), fr_o, chs, RATE)
+            st_o = S.EncoderSettings(**kw)
+            so, stride_o, lens_o, _ = encode_device(ctx, torch, dev, bo, n_o, st_o, RATE)
+            _, _, _, ms_eo = encode_device(ctx, torch, dev, bo, n_o, st_o, RATE, so)
+            hd = so.view(n_o, stride_o)[:, :22].cpu().numpy()
+            ks = []
+            for _ in range(4):
+                g, ms = decode_device(ctx, so, stride_o, lens_o, hd, po, bo.spp, n_o)
+                ks.append(ms)
+            ms_do = float(np.mean(ks[1:]))
+            other.append({"channels": chs, "settings": kw, "streams": n_o, "seconds": 20,
+                          "encode_msamples_per_s": n_o * bo.spp / (ms_eo * 1e-3) / 1e6,
+                          "decode_msamples_per_s": n_o * bo.spp / (ms_do * 1e-3) / 1e6,
+                          "decode_hbm_frac": (float(lens_o.sum()) + 2.0 * n_o * bo.spp) / (ms_do * 1e-3) / 1e9 / hbm})
+            del bo, so
+        del po
+        torch.cuda.empty_cache()
+
+    # ---- one-chunk streaming seam: microseconds per make_chunk / decode_chunk call, next to the CPU's per-chunk time
+    latency = None
+    if info.rank == 0 and W == 1 and not args.skip_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import latency_probe as LP
+
+        latency = []
+        for vbr_l in (False, True):
+            row = LP.measure(ctx, CHANNELS, 40, vbr_l)
+            row["cpu"] = LP.cpu_reference(CHANNELS, vbr_l)
+            latency.append(row)
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same stream shape
     cpu = None
     if info.rank == 0 and W == 1 and not args.skip_cpu:
@@ -660,7 +700,7 @@ def main():
             "dtype": "i32", "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "host": host_info(), "parity": parity,
             "strong": strong, "decode_vbr3": vbr_dec, "decode_8ch_cbr4": mc_dec, "encode": encode, "e2e_encode": e2e_encode,
-            "sweep": sweep,
+            "sweep": sweep, "other_shapes": other, "streaming_latency": latency,
         }))
     ctx.close()
     dist.shutdown()
