@@ -34,7 +34,10 @@ __device__ __forceinline__ void put_bits(uint32_t base, uint32_t pos, uint32_t n
     // and one unconditional pair of reductions is cheaper than a divergent branch)
     const uint64_t v64 = (uint64_t)value << (64u - off - n);
     red_or_shared(base + word * 4u, (uint32_t)(v64 >> 32));
-    if (off + n > 32u) red_or_shared(base + word * 4u + 4u, (uint32_t)v64);
+#ifdef SEA_ENC_COND_RED
+    if (off + n > 32u)
+#endif
+    red_or_shared(base + word * 4u + 4u, (uint32_t)v64);  // zero unless the field straddles (the image has two spare words)
 }
 __device__ __forceinline__ void put_byte(uint32_t base, uint32_t byte_off, uint32_t v) { put_bits(base, byte_off * 8u, 8u, v & 0xffu); }
 
@@ -273,7 +276,17 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                                  int16_t *xbuf_all)
 {
     constexpr uint32_t s = 4, nsf = 16, lpc = 16, cpw = 2;
-    const uint32_t C = p.channels, F = p.F;
+    // scale_factor_frames is the default 20 on this path (launch_encode_generic sends everything else to search_pass).  As a
+    // runtime value it costs a software division and several constant-bank reloads per block (40 of ~310 per-block instructions
+    // in profiles/r02_enc_cbr3_128_v2_*), so the direct-quantiser instances see it as a constant (-2.5 % at CBR-3).  The
+    // table-quantiser instances do NOT: with the constant ptxas schedules their trial 6-8 % slower (same-box A/B,
+    // profiles/r02_encode_ab.txt), so they keep reading p.F.
+#ifndef SEA_ENC_CONSTF_MASK
+#define SEA_ENC_CONSTF_MASK 0x0eu  /* bit FB: FB = 1, 2, 3 (VBR, FB = 0, measured a shade faster with the runtime value) */
+#endif
+    constexpr bool kConstF = FB >= 0 && ((SEA_ENC_CONSTF_MASK >> (FB < 0 ? 0 : FB)) & 1u) != 0u;
+    const uint32_t F = kConstF ? 20u : p.F;
+    const uint32_t C = p.channels;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t grp = lane >> 4, sf = lane & 15u;
     // p.split (few streams, launch_encode_generic): ONE channel per warp -- BASELINE's "one warp per (stream, channel)".  A warp's
@@ -553,11 +566,18 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             // REDUX min-reductions -- high word, low word, order -- need a third of the instructions but measured 5 % slower at
             // 1024 streams: their latency sits on the per-block critical path of a latency-bound kernel.)
             uint32_t g_lane;
-            if (!__any_sync(0xffffffffu, (rank >> 27) != 0ull)) {
-                // ordinary audio: every rank of the block is below 2^27, (rank, ord) fits 31 bits and ONE redux.sync per chain group
-                // finds the minimum (the 64-bit butterfly below is four dependent shuffle rounds, ~8 % of a latency-bound block)
-                const uint32_t key = ((uint32_t)rank << 4) | ord;
-                const uint32_t best = __reduce_min_sync(0xffffu << (grp * 16u), key);
+            // Ordinary audio: the WINNING rank is far below 2^27 (the losers of a block -- scale factors that clip -- are not), so ranks
+            // are clamped to 2^27 - 1, (rank, ord) fits 31 bits and ONE redux.sync per chain group finds the minimum; a clamped
+            // minimum (every candidate >= 2^27 - 1) takes the exact 64-bit butterfly below instead (four dependent shuffle rounds,
+            // ~8 % of a latency-bound block).
+            constexpr uint32_t kSat = (1u << 27) - 1u;
+            const uint32_t rank27 = (rank >> 27) != 0ull ? kSat : (uint32_t)rank;
+            const uint32_t best = __reduce_min_sync(0xffffu << (grp * 16u), (rank27 << 4) | ord);
+#ifdef SEA_ENC_OLD_ARGMIN
+            if (false) {
+#else
+            if (!__any_sync(0xffffffffu, (best >> 4) == kSat)) {
+#endif
                 g_lane = grp * 16u + ((best + prev) & (nsf - 1u));
             } else if (!__any_sync(0xffffffffu, (rank >> 60) != 0ull)) {
                 // the usual case: (rank, ord) fits one 64-bit key, a butterfly of 64-bit minima finds the winner's order and
@@ -1016,7 +1036,7 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     if (p.n_streams == 0) return cudaSuccess;
     const uint32_t nsf = 1u << p.s, lpc = nsf < 32u ? nsf : 32u, cpw = 32u / lpc;
     // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
-    const bool fast = p.s == 4u && p.F <= 32u && p.channels <= 16u;
+    const bool fast = p.s == 4u && p.F == 20u && p.channels <= 16u;
     // Few streams (BASELINE config 5 sharded over 8 GPUs: 128 per GPU): a warp per channel instead of per channel pair, while
     // that still leaves every warp a sub-partition of its own (see search_pass_fast)
     int dev = 0, sms = 148;
