@@ -202,6 +202,42 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     const uint32_t n_streams = (uint32_t)job.streams.size();
     if (job.total_chains == 0) return SEA_B200_OK;
 
+    // ---- small jobs (the one-chunk seam, a few chunks per call, one short file): one warp per chunk, decode_latency.cu.  The
+    // lane-per-chunk kernels below need tens of thousands of chunks to fill the GPU; under a few waves of warp-sized CTAs the
+    // serial chain of a chunk is what the caller waits for.  SEA_B200_DEC_LATENCY = 0 / 1 pins the choice (tests, tuning).
+    if (job.uniform) {
+        const size_t smem_l = decode_latency_smem(job.first.chunk_size, job.first.frames_per_chunk, job.first.channels);
+        const uint64_t chunks = job.total_chains / job.first.channels;
+        bool latency = false;
+        if (smem_l) {
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            const uint64_t per_sm = std::min<uint64_t>(32, (227u * 1024u) / (smem_l + 1024u));
+            // measured crossover against the throughput kernels (profiles/r02_decode_route_probe.txt): ~2.5 waves of these CTAs,
+            // stereo (2500 of 888 chunks per wave) and 8 channels (888 of 296) alike
+            latency = chunks * 2u <= (uint64_t)sms * per_sm * 5u;
+            if (const char *env = getenv("SEA_B200_DEC_LATENCY")) latency = env[0] == '1';
+        }
+        if (latency) {
+            CU(L.table->reserve(sizeof(DecStream) * n_streams));
+            CU(cudaMemcpyAsync(L.table->p, job.streams.data(), sizeof(DecStream) * n_streams, cudaMemcpyHostToDevice, L.stream));
+            CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
+            CU(cudaEventRecord(L.ev0, L.stream));
+            CU(launch_decode_latency(d_sea, d_pcm, L.table->as<DecStream>(), n_streams, chunks, job.first.chunk_size, job.first.frames_per_chunk,
+                                     job.first.channels, ctx->tabs, L.d_err, L.stream));
+            ctx->launches++;
+            CU(cudaEventRecord(L.ev1, L.stream));
+            int dev_err = 0;
+            CU(cudaMemcpyAsync(&dev_err, L.d_err, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+            CU(cudaStreamSynchronize(L.stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, L.ev0, L.ev1);
+            L.kernel_ms = ms;
+            ctx->last_kernel_ms = ms;
+            return map_dev_error(ctx, dev_err);
+        }
+    }
+
     DecFastParams fp = {};
     bool fast = false;
     if (job.uniform && have_hdr_word && (reinterpret_cast<uint64_t>(d_sea) & 15u) == 0) {

@@ -34,9 +34,6 @@ __device__ __forceinline__ void put_bits(uint32_t base, uint32_t pos, uint32_t n
     // and one unconditional pair of reductions is cheaper than a divergent branch)
     const uint64_t v64 = (uint64_t)value << (64u - off - n);
     red_or_shared(base + word * 4u, (uint32_t)(v64 >> 32));
-#ifdef SEA_ENC_COND_RED
-    if (off + n > 32u)
-#endif
     red_or_shared(base + word * 4u + 4u, (uint32_t)v64);  // zero unless the field straddles (the image has two spare words)
 }
 __device__ __forceinline__ void put_byte(uint32_t base, uint32_t byte_off, uint32_t v) { put_bits(base, byte_off * 8u, 8u, v & 0xffu); }
@@ -573,11 +570,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             constexpr uint32_t kSat = (1u << 27) - 1u;
             const uint32_t rank27 = (rank >> 27) != 0ull ? kSat : (uint32_t)rank;
             const uint32_t best = __reduce_min_sync(0xffffu << (grp * 16u), (rank27 << 4) | ord);
-#ifdef SEA_ENC_OLD_ARGMIN
-            if (false) {
-#else
             if (!__any_sync(0xffffffffu, (best >> 4) == kSat)) {
-#endif
                 g_lane = grp * 16u + ((best + prev) & (nsf - 1u));
             } else if (!__any_sync(0xffffffffu, (rank >> 60) != 0ull)) {
                 // the usual case: (rank, ord) fits one 64-bit key, a butterfly of 64-bit minima finds the winner's order and

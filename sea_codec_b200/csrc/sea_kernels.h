@@ -59,6 +59,13 @@ bool decode_mc_supported(const DecFastParams &p);
 cudaError_t launch_decode_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
                              int *d_err, cudaStream_t stream);
 
+// Small jobs (decode_latency.cu): one warp per chunk, any per-chunk header, <= 32 channels; every stream of the launch must share
+// chunk_size / frames_per_chunk / channels.  decode_latency_smem() == 0: geometry not supported.
+size_t decode_latency_smem(uint32_t chunk_size, uint32_t frames_per_chunk, uint32_t channels);
+cudaError_t launch_decode_latency(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, uint32_t n_streams, uint64_t total_chunks,
+                                  uint32_t chunk_size, uint32_t frames_per_chunk, uint32_t channels, DevTables tabs, int *d_err,
+                                  cudaStream_t stream);
+
 // Warps per CTA for the lane-per-chunk kernels (one full-width CTA per SM is their design point).  A grid of only a few waves
 // of such CTAs ends with most SMs idle while the last wave drains (BASELINE config 3 shape: 2.5 waves -> 16 % lost), so short
 // grids are cut into narrower CTAs -- the same warps per SM, several CTAs resident -- until the tail is a small share.

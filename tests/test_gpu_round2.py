@@ -377,3 +377,62 @@ def test_multi_gpu_batch_calls_equal_the_single_gpu_result(ctx, oracle):
             m.close()
     with pytest.raises(S.SeaError):
         S.MultiContext([99])
+
+
+# ------------------------------------------------------------------------------------------------ small-job decode kernel
+
+import test_gpu_next_rows as _R  # noqa: E402
+import test_gpu_parity as _P  # noqa: E402
+
+
+@pytest.mark.latency_kernel
+def test_latency_kernel_golden_and_errors(ctx, oracle):
+    _P.test_golden_decode(ctx)
+    _P.test_decode_errors(ctx, oracle)
+    _P.test_decode_ragged_lengths(ctx, oracle)
+    _R.test_vbr_corrupt_size_codes_match_the_generic_verdict(ctx, oracle)
+    _R.test_decode_range_random_access(ctx, oracle)
+
+
+@pytest.mark.latency_kernel
+@pytest.mark.parametrize("channels", [1, 2, 3, 8])
+def test_latency_kernel_cbr_and_vbr(ctx, oracle, channels):
+    for bits in range(1, 9):
+        _P.test_decode_cbr_matches_oracle(ctx, oracle, channels, bits)
+    if channels <= 2:
+        for bits in (1.5, 3.0, 4.5, 6.0, 7.3):
+            _P.test_decode_vbr_matches_oracle(ctx, oracle, channels, bits)
+    if channels in (1, 2, 3, 8):
+        _R.test_gpu_cbr_decode_against_the_reference_c_decoder(ctx, oracle, channels, 3 if channels != 8 else 4)
+
+
+@pytest.mark.latency_kernel
+def test_latency_kernel_geometries_and_corruption(ctx, oracle):
+    for sfb, sff, fpc in ((3, 20, 5120), (5, 20, 5120), (4, 10, 1000), (4, 5, 200), (2, 16, 4096), (6, 32, 320)):
+        _P.test_decode_other_geometry(ctx, oracle, sfb, sff, fpc)
+    _R.test_randomised_settings_against_oracle(ctx, oracle)
+    _R.test_corrupted_files_never_disagree_with_the_oracle(ctx, oracle)
+    _R.test_multi_chunk_streaming_equals_chunk_at_a_time(ctx, oracle, False)
+    _R.test_multi_chunk_streaming_equals_chunk_at_a_time(ctx, oracle, True)
+    for channels, kw in ((2, dict(residual_bits=3.0)), (2, dict(residual_bits=3.0, vbr=True)), (8, dict(residual_bits=4.0))):
+        test_truncated_stream_in_the_middle_of_a_batch(ctx, oracle, channels, kw)
+        test_crafted_small_header_chunk_size(ctx, oracle, channels, kw)
+
+
+@pytest.mark.auto_route
+def test_decode_route_is_chosen_by_job_size(ctx, oracle):
+    """Unpinned: one file (3 chunks) takes the small-job kernel, a batch of 400 x 20 chunks the throughput kernels; both must
+    match the oracle, and the launch counter tells the routes apart (one launch against full-chunk + partial-chunk kernels)."""
+    pcm = synth.gen_stream(71, 5120 * 2 + 700, 2, 44100)
+    enc = oracle.sea_encode(pcm, 44100, 2, oracle.make_settings(3.0))
+    want = oracle.sea_decode(enc).samples
+    n0 = ctx.launch_count
+    assert np.array_equal(ctx.sea_decode(enc).samples, want)
+    assert ctx.launch_count - n0 == 1
+    long = oracle.sea_encode(synth.gen_stream(72, 5120 * 20 + 700, 2, 44100), 44100, 2, oracle.make_settings(3.0))
+    want_long = oracle.sea_decode(long).samples
+    n0 = ctx.launch_count
+    got = ctx.decode_batch([long] * 400)
+    assert ctx.launch_count - n0 == 2
+    for g in (got[0], got[199], got[399]):
+        assert np.array_equal(g.samples, want_long)

@@ -31,16 +31,18 @@ def measure(ctx, channels=2, reps=60, vbr=False, bits=3.0):
     d = C.c_void_p()
     assert L.sea_b200_decoder_create(ctx._h, hdr.ctypes.data, 22, C.byref(d)) == 0
     dec = np.zeros(5120 * channels, dtype=np.int16)
-    dec_us = []
+    dec_us, k_ms = [], []
     for ck in chunks:
         t0 = time.perf_counter()
         rc = L.sea_b200_decoder_decode_chunk(d, ck.ctypes.data, ck.size, -1, dec.ctypes.data, dec.size, C.byref(n))
         dec_us.append((time.perf_counter() - t0) * 1e6)
+        k_ms.append(ctx.last_kernel_ms)
         assert rc == 0 and n.value == 5120 * channels
     L.sea_b200_decoder_destroy(d)
     return {"channels": channels, "vbr": vbr, "residual_bits": bits, "calls": reps,
             "make_chunk_us_median": float(np.median(enc_us[5:])), "make_chunk_us_p90": float(np.percentile(enc_us[5:], 90)),
             "decode_chunk_us_median": float(np.median(dec_us[5:])), "decode_chunk_us_p90": float(np.percentile(dec_us[5:], 90)),
+            "decode_kernel_us_median": float(np.median(k_ms[5:])) * 1e3,
             "chunk_bytes": int(cs), "frames_per_chunk": 5120}
 
 
