@@ -167,13 +167,14 @@ decode_staged_kernel(const uint8_t *__restrict__ sea, uint64_t sea_len, int16_t 
     uint64_t *row_a = row_in + Cfg::kRows;
 
     const uint32_t j = lane / C, c = lane % C;
+    const bool lane_ok = j < (uint32_t)Cfg::kRows;  // channel counts that do not divide 32 leave the last lanes without a chunk
     const uint64_t g = ((uint64_t)blockIdx.x * kWarpsPerCta + warp) * Cfg::kRows + j;  // global chunk index
     uint32_t frames = 0, F = p.F, b = p.b;
     uint64_t res_off = 0, sf_off = 0, vbr_off = 0, res_bits_avail = 0;
     int32_t w[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
     int16_t *out = pcm;
     bool vbr = false;
-    if (g < p.total_chunks) {
+    if (lane_ok && g < p.total_chunks) {
         const DecStream st = streams[find_stream(streams, p.n_streams, g * C)];
         const uint32_t k = (uint32_t)(g - st.chain_begin / C);
         const uint64_t ck_rel = (uint64_t)k * p.chunk_size;
@@ -214,7 +215,7 @@ decode_staged_kernel(const uint8_t *__restrict__ sea, uint64_t sea_len, int16_t 
     }
     int32_t sg[4];
     lms_signs(sg, h);
-    if (c == 0) {
+    if (c == 0 && lane_ok) {
         row_out[j] = reinterpret_cast<uint64_t>(out);
         row_in[j] = res_off;
     }
@@ -236,7 +237,7 @@ decode_staged_kernel(const uint8_t *__restrict__ sea, uint64_t sea_len, int16_t 
         // ---- stage the next slice of every row's packed residuals (coalesced 128-bit loads, byte-swapped to
         //      big-endian words so that MSB-first fields become plain shifts)
         const uint64_t a_mine = (res_off + (rowpos >> 3)) & ~(uint64_t)15;
-        if (c == 0) row_a[j] = a_mine;
+        if (c == 0 && lane_ok) row_a[j] = a_mine;
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < (Cfg::kRows * Cfg::kInVecs + 31) / 32; i++) {
@@ -328,12 +329,13 @@ decode_staged_kernel(const uint8_t *__restrict__ sea, uint64_t sea_len, int16_t 
         // ---- coalesced copy-out: each row's tile is one contiguous run of interleaved i16
         {
             const uint32_t tile_all = __shfl_sync(0xffffffffu, tile, 0);  // fast path when every row is full
-            uint32_t uniform = __all_sync(0xffffffffu, tile == tile_all) && tile_all == (uint32_t)Cfg::kTileFrames;
+            uint32_t uniform = __all_sync(0xffffffffu, tile == tile_all || !lane_ok) && tile_all == (uint32_t)Cfg::kTileFrames;
             const uint64_t round_off = (uint64_t)r * Cfg::kTileFrames * C;  // samples
             if (uniform) {
 #pragma unroll
-                for (int i = 0; i < (Cfg::kRows * Cfg::kOutVecs) / 32; i++) {
+                for (int i = 0; i < (Cfg::kRows * Cfg::kOutVecs + 31) / 32; i++) {
                     const int v = lane + 32 * i;
+                    if (v >= Cfg::kRows * Cfg::kOutVecs) break;  // row counts that do not tile the warp (3, 5, 7 channels)
                     const int row = v / Cfg::kOutVecs, col = v % Cfg::kOutVecs;
                     int16_t *dst = reinterpret_cast<int16_t *>(row_out[row]) + round_off;
                     const uint4 q = *reinterpret_cast<const uint4 *>(out_rows + row * Cfg::kOutPitch + col * 16);
@@ -379,7 +381,8 @@ static cudaError_t launch_staged(const uint8_t *d_sea, uint64_t sea_len, int16_t
 
 bool decode_fast_supported(const DecFastParams &p)
 {
-    if (p.channels != 1 && p.channels != 2) return false;
+    // 1, 2 and the odd counts the whole-frame kernel of decode_mc.cu does not take (3 is what the reference's tests use, tests/test.rs:10)
+    if (p.channels != 1 && p.channels != 2 && p.channels != 3 && p.channels != 5 && p.channels != 7) return false;
     if (p.s < 1 || p.s > 5) return false;  // 510 << s words of LUT must fit shared memory next to the tiles
     if (p.b < 1 || p.b > 8 || p.F == 0) return false;
     return true;
@@ -392,32 +395,30 @@ cudaError_t launch_decode_fast(const uint8_t *d_sea, uint64_t sea_len, int16_t *
     const int32_t *tab = tabs.by_s[p.s];
     const bool cbr = (p.hdr_word & 0xffu) == 1u;
 #define SEA_STAGED(CC, BB) return launch_staged<CC, BB>(d_sea, sea_len, d_pcm, d_streams, p, tab, d_err, stream)
-    if (p.channels == 1) {
-        if (!cbr) SEA_STAGED(1, 0);
-        switch (p.b) {
-            case 1: SEA_STAGED(1, 1);
-            case 2: SEA_STAGED(1, 2);
-            case 3: SEA_STAGED(1, 3);
-            case 4: SEA_STAGED(1, 4);
-            case 5: SEA_STAGED(1, 5);
-            case 6: SEA_STAGED(1, 6);
-            case 7: SEA_STAGED(1, 7);
-            default: SEA_STAGED(1, 8);
-        }
-    } else {
-        if (!cbr) SEA_STAGED(2, 0);
-        switch (p.b) {
-            case 1: SEA_STAGED(2, 1);
-            case 2: SEA_STAGED(2, 2);
-            case 3: SEA_STAGED(2, 3);
-            case 4: SEA_STAGED(2, 4);
-            case 5: SEA_STAGED(2, 5);
-            case 6: SEA_STAGED(2, 6);
-            case 7: SEA_STAGED(2, 7);
-            default: SEA_STAGED(2, 8);
-        }
+#define SEA_STAGED_C(CC)            \
+    {                               \
+        if (!cbr) SEA_STAGED(CC, 0); \
+        switch (p.b) {              \
+            case 1: SEA_STAGED(CC, 1); \
+            case 2: SEA_STAGED(CC, 2); \
+            case 3: SEA_STAGED(CC, 3); \
+            case 4: SEA_STAGED(CC, 4); \
+            case 5: SEA_STAGED(CC, 5); \
+            case 6: SEA_STAGED(CC, 6); \
+            case 7: SEA_STAGED(CC, 7); \
+            default: SEA_STAGED(CC, 8); \
+        }                           \
     }
+    switch (p.channels) {
+        case 1: SEA_STAGED_C(1)
+        case 2: SEA_STAGED_C(2)
+        case 3: SEA_STAGED_C(3)
+        case 5: SEA_STAGED_C(5)
+        default: SEA_STAGED_C(7)
+    }
+#undef SEA_STAGED_C
 #undef SEA_STAGED
 }
+
 
 }  // namespace sea

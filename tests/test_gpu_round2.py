@@ -436,3 +436,21 @@ def test_decode_route_is_chosen_by_job_size(ctx, oracle):
     assert ctx.launch_count - n0 == 2
     for g in (got[0], got[199], got[399]):
         assert np.array_equal(g.samples, want_long)
+
+
+# ------------------------------------------------------------------------------------------------ odd channel counts
+
+@pytest.mark.parametrize("channels", [3, 5, 7])
+def test_odd_channel_counts_take_the_staged_kernel(ctx, oracle, channels):
+    """3 (tests/test.rs:10), 5 and 7 channels: decode_staged_kernel with 32 / C chunks per warp and idle tail lanes -- uniform
+    batches, full and partial chunks, CBR at three sizes and VBR, against the oracle."""
+    for kw in (dict(residual_bits=1.0), dict(residual_bits=3.0), dict(residual_bits=8.0), dict(residual_bits=3.0, vbr=True),
+               dict(residual_bits=5.0, scale_factor_bits=5), dict(residual_bits=4.0, scale_factor_frames=10, frames_per_chunk=1000)):
+        fpc = kw.get("frames_per_chunk", 5120)
+        files = [oracle.sea_encode(synth.gen_stream(1000 + 10 * channels + i, fpc * 2 + 37 * i + (i % 2) * fpc, channels, 44100), 44100, channels,
+                                   oracle.make_settings(**kw)) for i in range(12)]
+        want = [oracle.sea_decode(f).samples for f in files]
+        n0 = ctx.launch_count
+        for g, w in zip(ctx.decode_batch(files), want):
+            assert np.array_equal(g.samples, w), (channels, kw)
+        assert ctx.launch_count - n0 == 1, "expected one staged-kernel launch"
