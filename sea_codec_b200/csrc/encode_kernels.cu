@@ -120,16 +120,20 @@ __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p,
                 const uint32_t ord = (sf - prev) & (nsf - 1u);  // position in the reference's rotated visiting order
                 const int32_t recip = __ldg(recips + sf);
                 const int32_t *row = rows + (sf << size);
-                int32_t w[4], h[4];
+                int32_t w[4], h[4], sg[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     w[i] = rw[i];
                     h[i] = rh[i];
                 }
+                lms_signs(sg, h);
                 unsigned long long rank = 0;
                 uint8_t *cbuf = codes + (size_t)cur_buf * F * T + threadIdx.x;
+                int32_t x_next = __ldg(x);  // the next frame's sample is requested a step ahead: its latency is off the chain
+#pragma unroll 4
                 for (uint32_t f = 0; f < nf; f++) {  // encoder_base.rs:64-89
-                    const int32_t xs = __ldg(x + (uint64_t)f * C);
+                    const int32_t xs = x_next;
+                    x_next = __ldg(x + (uint64_t)(f + 1u < nf ? f + 1u : f) * C);
                     const int32_t pr = lms_predict(w, h);
                     const int32_t r = (int32_t)((uint32_t)xs - (uint32_t)pr);
                     const uint32_t code = quant_code(r, recip, size);
@@ -137,7 +141,7 @@ __device__ void search_pass(int mode, uint32_t uniform_size, const EncParams &p,
                     const int32_t y = clamp_i16((int32_t)((uint32_t)pr + (uint32_t)d));
                     const int32_t e = xs - y;
                     rank += (unsigned long long)((long long)e * e) + lms_penalty(w);
-                    lms_update(w, h, y, d);
+                    lms_update_sg(w, h, sg, y, d);
                     cbuf[(size_t)f * T] = (uint8_t)code;
                 }
                 if (rank < best_rank || (rank == best_rank && ord < best_ord)) {
