@@ -1034,14 +1034,12 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     const uint32_t nsf = 1u << p.s, lpc = nsf < 32u ? nsf : 32u, cpw = 32u / lpc;
     // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
     const bool fast = p.s == 4u && p.F == 20u && p.channels <= 16u;
-    // Few streams (BASELINE config 5 sharded over 8 GPUs: 128 per GPU): a warp per channel instead of per channel pair, while
-    // that still leaves every warp a sub-partition of its own (see search_pass_fast)
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    bool split = fast && p.channels >= 2u && (uint64_t)p.n_streams * p.channels <= 4ull * (uint64_t)sms;
-    if (const char *env = getenv("SEA_B200_ENC_SPLIT"))  // tests and tuning runs pin the mapping: 0 = channel pairs, 1 = one channel per warp
-        split = fast && p.channels >= 2u && env[0] == '1';
+    // BASELINE's north star maps "one warp per (stream, channel)".  Built and tested (EncParams::split, search_pass_fast), measured,
+    // and NOT selected by default: the two channels of a pair already run concurrently in the two half-warps of one warp and a
+    // warp's step costs the same issue slots with 16 or 32 active lanes, so at 128 streams both mappings take 92.1 / 93.1 ms and
+    // at 512 the split one is 25 % slower (profiles/r02_split_probe.txt).  SEA_B200_ENC_SPLIT=1 selects it (tests, tuning).
+    bool split = false;
+    if (const char *env = getenv("SEA_B200_ENC_SPLIT")) split = fast && p.channels >= 2u && env[0] == '1';
     uint32_t warps = split ? p.channels : (p.channels + cpw - 1u) / cpw;
     if (warps > 8u) warps = 8u;
     const uint32_t T = warps * 32u;

@@ -247,9 +247,9 @@ def test_encode_lane_mappings_agree_with_the_oracle(ctx, oracle, channels, pin_m
             assert ctx.sea_encode(pcm, 44100, channels, st) == ref, (kw, "split" if mode == "1" else "pairs")
 
 
-def test_encode_mapping_is_chosen_by_stream_count(ctx, oracle):
-    """No pinning: 8 stereo streams take the warp-per-channel mapping, 400 the warp-per-pair one (n_streams * channels against
-    4 x SMs); both batches must match the oracle stream by stream, streaming state included."""
+def test_encode_batches_small_and_large_match_the_oracle(ctx, oracle):
+    """No pinning (the warp-per-pair mapping is the default at every size): 8 and 400 stereo streams -- fewer and more warps than
+    sub-partitions -- must match the oracle stream by stream, VBR and CBR."""
     ch, frames = 2, 5120 + 640
     st, ost = _settings_pair(oracle, residual_bits=3.0, vbr=True)
     uniq = [synth.gen_stream(500 + i, frames, ch, 44100) for i in range(8)]
