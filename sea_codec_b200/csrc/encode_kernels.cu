@@ -228,7 +228,8 @@ __host__ __device__ inline uint32_t enc_lut_entries(int fb, uint32_t vbr_base)  
 }
 // CBR: a function of the residual size alone (compile-time in encode_kernel<FB>); VBR: chosen by the host from the CTA's total
 // shared memory (launch_encode_generic) and passed in EncParams::lut_mode.
-__host__ __device__ constexpr int enc_lut_mode_cbr(int fb) { return fb <= 7 ? kEncLut32 : kEncLut16; }
+// (scale_factor_bits other than 4: the [code][16] layout does not apply; size 8 reads the table through L1)
+__host__ __device__ constexpr int enc_lut_mode_cbr(int fb, int S = 4) { return fb <= 7 ? kEncLut32 : (S == 4 ? kEncLut16 : kEncLutGlobal); }
 template <int M>
 struct LutTag {
     static constexpr int value = M;
@@ -270,13 +271,16 @@ struct FastLut {
 
 constexpr uint32_t kCodePitch = 36;  // bytes between the frame rows of a warp's code buffer (search_pass_fast)
 
-template <int FB>
+// S = scale_factor_bits (3, 4 or 5: what seaconv accepts, seaconv.rs:35-41): 2^S candidates per chain = lanes per chain group,
+// 32 / 2^S chains per warp.
+template <int FB, int S>
 __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParams &p, const int16_t *__restrict__ x0, uint32_t frames,
                                  const int32_t *__restrict__ tab, int32_t *st_w, int32_t *st_h, int32_t *st_prev, uint8_t *codes,
                                  uint32_t chunk_buf, uint32_t sf_sec_bit, uint32_t res_sec_bit, const VbrScratch &vs, const FastLut &fl,
                                  int16_t *xbuf_all)
 {
-    constexpr uint32_t s = 4, nsf = 16, lpc = 16, cpw = 2;
+    constexpr uint32_t s = S, nsf = 1u << S, lpc = nsf, cpw = 32u / lpc;
+    constexpr uint32_t kGroupMask = lpc == 32u ? 0xffffffffu : (1u << (lpc & 31u)) - 1u;
     // scale_factor_frames is the default 20 on this path (launch_encode_generic sends everything else to search_pass).  As a
     // runtime value it costs a software division and several constant-bank reloads per block (40 of ~310 per-block instructions
     // in profiles/r02_enc_cbr3_128_v2_*), so the direct-quantiser instances see it as a constant (-2.5 % at CBR-3).  The
@@ -289,7 +293,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
     const uint32_t F = kConstF ? 20u : p.F;
     const uint32_t C = p.channels;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t grp = lane >> 4, sf = lane & 15u;
+    const uint32_t grp = lane / lpc, sf = lane & (lpc - 1u);
     // p.split (few streams, launch_encode_generic): ONE channel per warp -- BASELINE's "one warp per (stream, channel)".  A warp's
     // step costs the same issue slots whether 16 or 32 of its lanes carry a chain, and with fewer warps than sub-partitions
     // every warp runs alone at its own latency, so halving the chains per warp halves the time.  Both lane groups then run the
@@ -310,8 +314,8 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             const uint32_t nf0 = frames < F ? frames : F;
             if (lane < nf0) {
                 const int16_t *px = x0 + (uint64_t)lane * C;
-                xbuf[lane] = __ldg(px + cb);
-                xbuf[F + lane] = __ldg(px + (cb + 1u < C ? cb + 1u : C - 1u));
+#pragma unroll
+                for (uint32_t q = 0; q < cpw; q++) xbuf[q * F + lane] = __ldg(px + (cb + q < C ? cb + q : C - 1u));
             }
         }
         __syncwarp();
@@ -340,7 +344,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
         int32_t mag_by[3][4] = {};  // [size - 1][level]
         auto direct_setup = [&](uint32_t z, uint32_t rc, uint32_t *th, int32_t *mg) {
             const uint32_t levels = z == 3u ? 3u : (z == 2u ? 1u : 0u);
-            const int32_t *row0 = tab + tab_dqt_off(4, z) + (sf << z);
+            const int32_t *row0 = tab + tab_dqt_off(s, z) + (sf << z);
 #pragma unroll
             for (uint32_t j = 0; j < 4u; j++)
                 if (j <= levels) mg[j] = __ldg(row0 + 2u * j);  // dqt[sf][2k] = +round(sf * curve[k]) (dqt.rs:114-123)
@@ -356,20 +360,20 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
         if (FB == 0) {
 #pragma unroll
             for (uint32_t z = 1; z <= 3u; z++)
-                if (z >= fl.lo_size && z <= fl.lo_size + 3u) direct_setup(z, (uint32_t)fl.recip[(z - fl.lo_size) * 16u + sf], theta_by[z - 1u], mag_by[z - 1u]);
+                if (z >= fl.lo_size && z <= fl.lo_size + 3u) direct_setup(z, (uint32_t)fl.recip[(z - fl.lo_size) * nsf + sf], theta_by[z - 1u], mag_by[z - 1u]);
         }
         uint32_t spec_skip = 0;  // blocks left before the 32-bit penalty form is tried again after a failed proof
         for (uint32_t blk = 0; blk < nblk; blk++) {
             uint32_t nf = frames - blk * F;
             if (nf > F) nf = F;
             // prefetch the next block's samples into registers; they land in shared memory after this block's steps
-            int32_t nx0 = 0, nx1 = 0;
+            int32_t nx[cpw];
             const uint32_t next_frame = (blk + 1u) * F + lane;
             const bool pre = blk + 1u < nblk && lane < F && next_frame < frames;
             if (pre) {
                 const int16_t *px = x0 + (uint64_t)next_frame * C;
-                nx0 = __ldg(px + cb);
-                nx1 = __ldg(px + (cb + 1u < C ? cb + 1u : C - 1u));
+#pragma unroll
+                for (uint32_t q = 0; q < cpw; q++) nx[q] = __ldg(px + (cb + q < C ? cb + q : C - 1u));
             }
             uint32_t bdesc = 0;  // second VBR pass: size | prefix << 4 | frame bits << 12 of this (block, channel)
             if (FB == 0 && mode == 2) {
@@ -378,11 +382,11 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             }
             const uint32_t size = FB > 0 ? (uint32_t)FB : (mode == 2 ? (bdesc & 15u) : uniform_size);
             const uint32_t slot = FB > 0 ? 0u : size - fl.lo_size;
-            const int32_t recip = fl.recip[slot * 16u + sf];
+            const int32_t recip = fl.recip[slot * nsf + sf];
             // shared [code][lane] / [code][sf] (two chains share a row) / global [sf][code]: see kEncLut*
             // Two separate views: a global pointer and a 32-bit shared-window address.  (One pointer selected between the two
             // made the VBR kernel's table reads generic LD.E -- long-scoreboard latency on the step's critical path.)
-            const int32_t *row = tab + tab_dqt_off(4, size) + (sf << size);
+            const int32_t *row = tab + tab_dqt_off(s, size) + (sf << size);
             const uint32_t row_sh = fl.lut_sh + 4u * (fl.mode == kEncLut32 ? fl.slot_off(size) + lane : (fl.slot_off(size) >> 1) + sf);
             const uint32_t kmax = (1u << (size - 1u)) - 1u;
 
@@ -558,7 +562,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 else if (narrow) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<0>{}, direct_tag);
                 else trial(RankTag<kRankWide>{}, lut_tag, LutTag<0>{}, direct_tag);
             };
-            if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1)>{}, LutTag<kDirect ? 1 : 0>{});
+            if (FB > 0) run(LutTag<enc_lut_mode_cbr(FB > 0 ? FB : 1, S)>{}, LutTag<kDirect ? 1 : 0>{});
             else if (direct_now) run(LutTag<kEncLut32>{}, LutTag<1>{});  // no table on this path
             else if (fl.mode == kEncLut32) run(LutTag<kEncLut32>{}, LutTag<0>{});
             else if (fl.mode == kEncLut16) run(LutTag<kEncLut16>{}, LutTag<0>{});
@@ -573,19 +577,19 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
             // ~8 % of a latency-bound block).
             constexpr uint32_t kSat = (1u << 27) - 1u;
             const uint32_t rank27 = (rank >> 27) != 0ull ? kSat : (uint32_t)rank;
-            const uint32_t best = __reduce_min_sync(0xffffu << (grp * 16u), (rank27 << 4) | ord);
-            if (!__any_sync(0xffffffffu, (best >> 4) == kSat)) {
-                g_lane = grp * 16u + ((best + prev) & (nsf - 1u));
-            } else if (!__any_sync(0xffffffffu, (rank >> 60) != 0ull)) {
+            const uint32_t best = __reduce_min_sync(kGroupMask << (grp * (lpc & 31u)), (rank27 << s) | ord);
+            if (!__any_sync(0xffffffffu, (best >> s) == kSat)) {
+                g_lane = grp * lpc + ((best + prev) & (nsf - 1u));
+            } else if (!__any_sync(0xffffffffu, (rank >> (64u - s)) != 0ull)) {
                 // the usual case: (rank, ord) fits one 64-bit key, a butterfly of 64-bit minima finds the winner's order and
                 // the lane follows from it: sf = (ord + prev) mod 16 (encoder_base.rs:116-117)
-                unsigned long long key = (rank << 4) | ord;
+                unsigned long long key = (rank << s) | ord;
 #pragma unroll
                 for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
                     const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                     key = other < key ? other : key;
                 }
-                g_lane = grp * 16u + (((uint32_t)key + prev) & (nsf - 1u));
+                g_lane = grp * lpc + (((uint32_t)key + prev) & (nsf - 1u));
             } else {  // ranks of 2^60 and more (runaway weights penalty): compare (rank, ord) explicitly
                 unsigned long long g_rank = rank;
                 g_lane = lane;
@@ -593,7 +597,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 for (uint32_t o = lpc >> 1; o > 0; o >>= 1) {
                     const unsigned long long o_rank = __shfl_xor_sync(0xffffffffu, g_rank, o);
                     const uint32_t o_lane = __shfl_xor_sync(0xffffffffu, g_lane, o);
-                    const uint32_t g_ord = ((g_lane & 15u) - prev) & (nsf - 1u), o_ord = ((o_lane & 15u) - prev) & (nsf - 1u);
+                    const uint32_t g_ord = ((g_lane & (lpc - 1u)) - prev) & (nsf - 1u), o_ord = ((o_lane & (lpc - 1u)) - prev) & (nsf - 1u);
                     if (o_rank < g_rank || (o_rank == g_rank && o_ord < g_ord)) {
                         g_rank = o_rank;
                         g_lane = o_lane;
@@ -606,47 +610,51 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 cw[i] = __shfl_sync(0xffffffffu, w[i], g_lane);
                 chh[i] = __shfl_sync(0xffffffffu, h[i], g_lane);
             }
-            prev = g_lane & 15u;
+            prev = g_lane & (lpc - 1u);
             if (active && lane == g_lane) {
                 if (mode == 1) vs.keys[blk * C + c] = rank;
                 else put_bits(chunk_buf, sf_sec_bit + (blk * C + c) * s, s, sf);
             }
             if (mode != 1) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
-                // One lane per FRAME: the codes of the warp's two channels are adjacent bits of the frame's row, so lane f reads both
-                // winners' codes and writes them as one field (it was one lane per code: two divergent rounds of put_bits per
-                // block -- 14 % of the stall samples of profiles/r02_enc_cbr3_128_*).
-                const uint32_t g0 = __shfl_sync(0xffffffffu, g_lane, 0), g1 = __shfl_sync(0xffffffffu, g_lane, 16);
-                const bool two = !split && cb + 1u < C;  // group 1 carries a real channel
-                uint32_t blockbit, rowbits, prefix0, size0, size1;
+                // One lane per FRAME: the codes of the warp's channels are adjacent bits of the frame's row, so lane f reads every
+                // winner's code and writes them as one field of up to 32 bits (it was one lane per code: two divergent rounds of
+                // put_bits per block -- 14 % of the stall samples of profiles/r02_enc_cbr3_128_*).
+                const uint32_t nch = split ? 1u : (C - cb < cpw ? C - cb : cpw);  // chain groups of this warp that carry a real channel
+                uint32_t gq[cpw], sq[cpw];
+                uint32_t blockbit, rowbits, prefix0;
                 if (mode == 2) {
                     if (vs.blkbit_sh) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(blockbit) : "r"(vs.blkbit_sh + blk * 4u));
                     else blockbit = vs.blkbit[blk];
-                    const uint32_t d0 = __shfl_sync(0xffffffffu, bdesc, 0), d1 = __shfl_sync(0xffffffffu, bdesc, 16);
+                    const uint32_t d0 = __shfl_sync(0xffffffffu, bdesc, 0);
                     rowbits = d0 >> 12;
                     prefix0 = (d0 >> 4) & 255u;
-                    size0 = d0 & 15u;
-                    size1 = d1 & 15u;
                 } else {
                     rowbits = C * size;
                     blockbit = blk * F * rowbits;
                     prefix0 = cb * size;
-                    size0 = size1 = size;
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < cpw; q++) {
+                    gq[q] = __shfl_sync(0xffffffffu, g_lane, (q * lpc) & 31u);
+                    sq[q] = mode == 2 ? (__shfl_sync(0xffffffffu, bdesc, (q * lpc) & 31u) & 15u) : size;
                 }
                 __syncwarp();  // the winners' codes were written by other lanes
                 if (lane < nf) {
                     const uint8_t *row = codes + warp * (F * kCodePitch) + lane * kCodePitch;
-                    uint32_t field = row[g0], n = size0;
-                    if (two) {
-                        field = (field << size1) | row[g1];
-                        n += size1;
-                    }
+                    uint32_t field = 0, n = 0;
+#pragma unroll
+                    for (uint32_t q = 0; q < cpw; q++)
+                        if (q < nch) {
+                            field = (field << sq[q]) | row[gq[q]];
+                            n += sq[q];
+                        }
                     put_bits(chunk_buf, res_sec_bit + blockbit + lane * rowbits + prefix0, n, field);
                 }
             }
             __syncwarp();  // everybody is done with this block's samples and codes
             if (pre) {
-                xbuf[lane] = (int16_t)nx0;
-                xbuf[F + lane] = (int16_t)nx1;
+#pragma unroll
+                for (uint32_t q = 0; q < cpw; q++) xbuf[q * F + lane] = (int16_t)nx[q];
             }
             __syncwarp();
         }
@@ -751,7 +759,7 @@ __device__ bool warp_sort_512(unsigned long long *keys, uint32_t *idx, uint32_t 
 }
 
 // FB = -1: generic search pass (any scale_factor_bits);  FB = 0: fast pass, runtime residual sizes (VBR);  FB = 1..8: fast pass, CBR.
-template <int FB>
+template <int FB, int S>
 __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const EncStream *__restrict__ streams,
                               EncParams p, DevTables tabs, int32_t *state, uint64_t *out_lens, uint32_t *chunk0,
                               unsigned long long *ties, EncWorkspace ws, int *err)
@@ -778,8 +786,9 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
     if (FB >= 0) {
         uint8_t *extra = codes + ((2u * (size_t)F * T + 15u) & ~(size_t)15u);
         xbuf = reinterpret_cast<int16_t *>(extra);
-        int32_t *rcp = reinterpret_cast<int32_t *>(extra + (((T >> 5) * 2u * F * 2u + 15u) & ~15u));
-        int32_t *lut = rcp + 64;
+        constexpr uint32_t kNsf = 1u << (S > 0 ? S : 4), kCpw = 32u / kNsf;
+        int32_t *rcp = reinterpret_cast<int32_t *>(extra + (((T >> 5) * kCpw * F * 2u + 15u) & ~15u));
+        int32_t *lut = rcp + 4u * kNsf;
         fl.lut = lut;
         fl.lut_sh = (uint32_t)__cvta_generic_to_shared(lut);
 #ifdef SEA_ENC_DEBUG_SPEC
@@ -787,19 +796,19 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
 #endif
         fl.recip = rcp;
         fl.lo_size = FB > 0 ? (uint32_t)FB : (p.base > 1u ? p.base - 1u : 1u);
-        fl.mode = FB > 0 ? enc_lut_mode_cbr(FB > 0 ? FB : 1) : (int)p.lut_mode;
+        fl.mode = FB > 0 ? enc_lut_mode_cbr(FB > 0 ? FB : 1, S) : (int)p.lut_mode;
         const uint32_t n_slots = FB > 0 ? 1u : 4u;
         uint32_t off = 0;
         for (uint32_t i = 0; i < n_slots; i++) {
             const uint32_t size = fl.lo_size + i;
             if (size <= 8u) {
-                for (uint32_t e = tid; e < 16u; e += T) rcp[i * 16u + e] = tab[tab_recip_off(4, size) + e];
-                if (fl.mode == kEncLut32) {
+                for (uint32_t e = tid; e < kNsf; e += T) rcp[i * kNsf + e] = tab[tab_recip_off(s, size) + e];
+                if (fl.mode == kEncLut32) {  // [code][32 lanes]: lane l looks its own scale factor l mod 2^S up
                     const uint32_t n = 32u << size;
-                    for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 5)];
-                } else if (fl.mode == kEncLut16) {
+                    for (uint32_t e = tid; e < n; e += T) lut[off + e] = tab[tab_dqt_off(s, size) + ((e & (kNsf - 1u)) << size) + (e >> 5)];
+                } else if (fl.mode == kEncLut16) {  // S == 4 only: [code][16 scale factors], shared by the two chains of a warp
                     const uint32_t n = 16u << size;
-                    for (uint32_t e = tid; e < n; e += T) lut[(off >> 1) + e] = tab[tab_dqt_off(4, size) + ((e & 15u) << size) + (e >> 4)];
+                    for (uint32_t e = tid; e < n; e += T) lut[(off >> 1) + e] = tab[tab_dqt_off(s, size) + ((e & 15u) << size) + (e >> 4)];
                 }
                 off += 32u << size;  // slot offsets are kept in [code][32] units; kEncLut16 halves them
             }
@@ -875,12 +884,12 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
         }
 
         if (!vbr) {
-            if (FB >= 0) search_pass_fast<FB>(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            if (FB >= 0) search_pass_fast<FB, (S > 0 ? S : 4)>(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
             else search_pass(0, p.hdr_bits, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
             if (tid == 0) sh_res_bits = frames * C * p.hdr_bits;
         } else {
             // ---- analysis at base+1 bits (encoder_vbr.rs:139-171); restores lms only (trap T2)
-            if (FB >= 0) search_pass_fast<FB>(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            if (FB >= 0) search_pass_fast<FB, (S > 0 ? S : 4)>(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
             else search_pass(1, p.base + 1u, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
             __syncthreads();
             for (uint32_t i = tid; i < 4 * C; i += T) {
@@ -966,7 +975,7 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
             }
             __syncthreads();
             // ---- second pass with the chosen sizes (encoder_vbr.rs:193-207)
-            if (FB >= 0) search_pass_fast<FB>(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
+            if (FB >= 0) search_pass_fast<FB, (S > 0 ? S : 4)>(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs, fl, xbuf);
             else search_pass(2, 0, p, x0, frames, tab, st_w, st_h, st_prev, codes, chunk_sh, sf_sec_bit, res_sec_bit, vs);
         }
         __syncthreads();
@@ -1011,18 +1020,18 @@ __global__ void encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restri
     }
 }
 
-template <int FB>
+template <int FB, int S>
 static cudaError_t launch_encode_t(const int16_t *d_pcm, uint8_t *d_out, const EncStream *d_streams, const EncParams &p, DevTables tabs,
                                    int32_t *d_state, uint64_t *d_out_lens, uint32_t *d_chunk0, unsigned long long *d_ties, EncWorkspace ws,
                                    int *d_err, cudaStream_t stream, uint32_t T, size_t smem)
 {
-    cudaError_t e = cudaFuncSetAttribute(encode_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(encode_kernel<FB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // one CTA per stream: residency is bounded by shared memory, so ask for the largest carve-out (the driver's default picked
     // 164 KB of the 228 KB and left a second wave at the high bitrates)
-    e = cudaFuncSetAttribute(encode_kernel<FB>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(encode_kernel<FB, S>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    encode_kernel<FB><<<p.n_streams, T, smem, stream>>>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err);
+    encode_kernel<FB, S><<<p.n_streams, T, smem, stream>>>(d_pcm, d_out, d_streams, p, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err);
     return cudaGetLastError();
 }
 
@@ -1032,8 +1041,9 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
 {
     if (p.n_streams == 0) return cudaSuccess;
     const uint32_t nsf = 1u << p.s, lpc = nsf < 32u ? nsf : 32u, cpw = 32u / lpc;
-    // fast pass: scale_factor_bits 4, a block's frames fit one lane each, every channel pair has its own warp
-    const bool fast = p.s == 4u && p.F == 20u && p.channels <= 16u;
+    // fast pass: scale_factor_bits 3, 4 or 5 (8 / 16 / 32 lanes per chain group), the default 20 frames per block, every group
+    // of 32 / 2^s channels has its own warp
+    const bool fast = p.s >= 3u && p.s <= 5u && p.F == 20u && p.channels <= 16u;
     // BASELINE's north star maps "one warp per (stream, channel)".  Built and tested (EncParams::split, search_pass_fast), measured,
     // and NOT selected by default: the two channels of a pair already run concurrently in the two half-warps of one warp and a
     // warp's step costs the same issue slots with 16 or 32 active lanes, so at 128 streams both mappings take 92.1 / 93.1 ms and
@@ -1046,7 +1056,7 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
     size_t smem = ((size_t)(p.max_chunk_bytes + 3u) / 4u + 2u) * 4u + (size_t)p.channels * 17u * 4u + ((2u * (size_t)p.F * T + 15u) & ~(size_t)15u) + 16u;
     int lut_mode = kEncLut32;
     if (fast) {
-        smem += ((size_t)warps * 2u * p.F * 2u + 15u) & ~(size_t)15u;
+        smem += ((size_t)warps * cpw * p.F * 2u + 15u) & ~(size_t)15u;
         {   // One CTA per stream, all of them resident at once if they fit: with k = ceil(streams / 148) CTAs per SM a CTA may use
             // 227 KB / k less the 1 KB the hardware reserves per CTA (31 KB at the benchmark's 1024 streams); with more streams
             // than that would leave 28 KB for, keep the CTA at or under 28 KB (8 per SM, several waves).
@@ -1055,13 +1065,13 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
             const size_t per_sm = (p.n_streams + 147u) / 148u;
             size_t budget = 227u * 1024u / per_sm;
             budget = budget > 1280u + 28u * 1024u ? budget - 1280u : 28u * 1024u;
-            if (!p.vbr) lut_mode = enc_lut_mode_cbr(fb);
+            if (!p.vbr) lut_mode = enc_lut_mode_cbr(fb, (int)p.s);
             else if (other + e * 128u <= budget) lut_mode = kEncLut32;
-            else if (other + e * 64u <= budget) lut_mode = kEncLut16;
+            else if (p.s == 4u && other + e * 64u <= budget) lut_mode = kEncLut16;
             else lut_mode = kEncLutGlobal;
             if (lut_mode != kEncLutGlobal) smem += e * (lut_mode == kEncLut32 ? 128u : 64u);
         }
-        smem += 64u * 4u;  // reciprocals [slot][16]
+        smem += 4u * nsf * 4u;  // reciprocals [slot][2^s]
     }
     EncParams pp = p;
     pp.vbr_smem_off = 0;
@@ -1076,19 +1086,28 @@ cudaError_t launch_encode_generic(const int16_t *d_pcm, uint8_t *d_out, const En
         }
     }
     if (smem > 200u * 1024u) return cudaErrorInvalidConfiguration;
-#define SEA_ENC(FBV) return launch_encode_t<FBV>(d_pcm, d_out, d_streams, pp, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err, stream, T, smem)
-    if (!fast) SEA_ENC(-1);
-    if (p.vbr) SEA_ENC(0);
-    switch (p.hdr_bits) {
-        case 1: SEA_ENC(1);
-        case 2: SEA_ENC(2);
-        case 3: SEA_ENC(3);
-        case 4: SEA_ENC(4);
-        case 5: SEA_ENC(5);
-        case 6: SEA_ENC(6);
-        case 7: SEA_ENC(7);
-        default: SEA_ENC(8);
+#define SEA_ENC(FBV, SV) return launch_encode_t<FBV, SV>(d_pcm, d_out, d_streams, pp, tabs, d_state, d_out_lens, d_chunk0, d_ties, ws, d_err, stream, T, smem)
+#define SEA_ENC_S(SV)                      \
+    {                                      \
+        if (p.vbr) SEA_ENC(0, SV);         \
+        switch (p.hdr_bits) {              \
+            case 1: SEA_ENC(1, SV);        \
+            case 2: SEA_ENC(2, SV);        \
+            case 3: SEA_ENC(3, SV);        \
+            case 4: SEA_ENC(4, SV);        \
+            case 5: SEA_ENC(5, SV);        \
+            case 6: SEA_ENC(6, SV);        \
+            case 7: SEA_ENC(7, SV);        \
+            default: SEA_ENC(8, SV);       \
+        }                                  \
     }
+    if (!fast) SEA_ENC(-1, 0);
+    switch (p.s) {
+        case 3: SEA_ENC_S(3)
+        case 5: SEA_ENC_S(5)
+        default: SEA_ENC_S(4)
+    }
+#undef SEA_ENC_S
 #undef SEA_ENC
 }
 

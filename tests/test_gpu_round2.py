@@ -454,3 +454,34 @@ def test_odd_channel_counts_take_the_staged_kernel(ctx, oracle, channels):
         for g, w in zip(ctx.decode_batch(files), want):
             assert np.array_equal(g.samples, w), (channels, kw)
         assert ctx.launch_count - n0 == 1, "expected one staged-kernel launch"
+
+
+# ------------------------------------------------------------------------------------------------ scale_factor_bits 3 and 5 on the fast pass
+
+@pytest.mark.parametrize("sfb", [3, 5])
+@pytest.mark.parametrize("channels", [1, 2, 3, 5, 8])
+def test_encode_fast_pass_other_scale_factor_bits(ctx, oracle, sfb, channels, pin_mapping):
+    """tests/test.rs:37 sweeps scale_factor_bits 3..5: 8 resp. 32 candidates per block = 8 / 32 lanes per chain group, four chains /
+    one chain per warp.  CBR 1..8 and VBR, ragged last chunk, batches of streams with different lengths, both lane mappings."""
+    frames = 5120 * 2 + 999
+    pcm = synth.gen_stream(40 + channels, frames, channels, 44100)
+    cases = [dict(residual_bits=float(b), scale_factor_bits=sfb) for b in range(1, 9)] + \
+            [dict(residual_bits=b, vbr=True, scale_factor_bits=sfb) for b in (2.0, 3.0, 4.5, 6.5)]
+    for kw in cases:
+        st, ost = _settings_pair(oracle, **kw)
+        try:
+            ref = oracle.sea_encode(pcm, 44100, channels, ost)
+        except oracle.OracleError:
+            with pytest.raises(S.SeaError):
+                ctx.sea_encode(pcm, 44100, channels, st)
+            continue
+        assert ctx.sea_encode(pcm, 44100, channels, st) == ref, kw
+    pin_mapping("1")
+    st, ost = _settings_pair(oracle, residual_bits=3.0, scale_factor_bits=sfb)
+    if channels >= 2:
+        assert ctx.sea_encode(pcm, 44100, channels, st) == oracle.sea_encode(pcm, 44100, channels, ost)
+    pin_mapping("0")
+    streams = [synth.gen_stream(60 + i, 5120 + 777 * i, channels, 44100) for i in range(5)]
+    for kw in (dict(residual_bits=3.0, scale_factor_bits=sfb), dict(residual_bits=3.5, vbr=True, scale_factor_bits=sfb)):
+        st, ost = _settings_pair(oracle, **kw)
+        assert ctx.encode_batch(streams, 44100, channels, st) == [oracle.sea_encode(x, 44100, channels, ost) for x in streams], kw
