@@ -246,9 +246,9 @@ struct LutTag {
 //                the candidate actually did: a weight moves by |d >> 4| <= (|d| >> 4) + 1 per frame (lms.rs:43-51), so
 //                max|w(0)| + (sum|d| >> 4) + 20 <= 32767 proves it for every frame of the block; the trajectory (codes, history,
 //                weights) never depends on the penalty arithmetic, only the rank does, and a block whose proof fails in any lane is
-//                simply run again in the 64-bit form.  With the direct quantiser (sizes 1-3) the lane's largest magnitude is a
-//                register and the bound sum_i (|w_i| + 20 * max|delta|)^2 < 2^32 is taken before the trial instead (it holds
-//                at ordinary weights there and costs nothing per step; for the larger sizes it never held).
+//                simply run again in the 64-bit form.  The CBR instances with the direct quantiser (sizes 1-3) take the bound
+//                sum_i (|w_i| + 20 * max|delta|)^2 < 2^32 before the trial instead (the lane's largest magnitude is a register;
+//                it holds at ordinary weights there and costs nothing per step; for the larger sizes it never held).
 enum : int { kRankWide = 0, kRankNarrow = 1, kRankSum32 = 2 };
 template <int V>
 struct RankTag {
@@ -452,6 +452,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                                 k2 = ge ? 2u * (uint32_t)(j + 1) : k2;
                             }
                         }
+                        if (kRank == kRankSum32 && !kDirect) dsum += (uint32_t)mg;       // |d|: the proof of the 32-bit penalty form (VBR)
                         d = (mg ^ ms) - ms;                                              // odd code = negative (dqt.rs:118-121)
                         code = k2 - (uint32_t)ms;                                        // 2k + (r < 0)
                     } else {
@@ -507,20 +508,22 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                     for (uint32_t f = 0; f < nf; f++) step(f);
                 }
             };
-            // per-block choice of the penalty form (warp-uniform: one code path per block)
-            const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
+            // Per-block choice of the penalty form.  The 32-bit form (kRankSum32) is always TRIED on a default block and proved
+            // afterwards from what the candidates did (one vote, shared with nothing else on the way in): the three votes that used
+            // to pick a form before the trial -- weights narrow? bound for the direct quantiser? weights small enough to try? -- sat
+            // on the block's critical path (~40 instructions and three vote latencies of a ~310-instruction epilogue).
             uint32_t m0 = 0;  // max |w_i| at the start of the block (|INT_MIN| wraps to 2^31: never below the limit)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint32_t a = w[i] < 0 ? 0u - (uint32_t)w[i] : (uint32_t)w[i];
                 m0 = a > m0 ? a : m0;
             }
-            // direct quantiser: the lane's largest magnitude is in a register, so the bound is taken before the trial (no per-step
-            // bookkeeping): sum_i (|w_i| + 20 * max|delta|)^2 < 2^32 keeps sum w^2 below 2^32 for the whole block
+            // CBR sizes 1..3 (direct quantiser in every block): the lane's largest magnitude is a register, so the bound
+            // sum_i (|w_i| + 20 * max|delta|)^2 < 2^32 is taken BEFORE the trial instead -- one vote, nothing per step (the
+            // per-step |d| accumulation of the proof costs these instances 1-2 % at 1024 streams; profiles/r02_encode_ab.txt)
             bool prior32 = false;
-            if (nf == 20u && direct_now) {
-                const int32_t top = FB == 0 ? (size == 3u ? mag[3] : (size == 2u ? mag[1] : mag[0])) : mag[kLevels];
-                const uint32_t grow = 20u * (((uint32_t)top + 15u) >> 4);
+            if (kDirect && nf == 20u) {
+                const uint32_t grow = 20u * (((uint32_t)mag[kLevels] + 15u) >> 4);
                 unsigned long long g = 0;
                 bool ok = true;
 #pragma unroll
@@ -531,8 +534,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 }
                 prior32 = __all_sync(0xffffffffu, ok && (g >> 32) == 0ull);
             }
-            // table quantiser: try the 32-bit form and prove it afterwards from sum |d| (see kRankSum32)
-            const bool try32 = nf == 20u && !direct_now && spec_skip == 0u && __all_sync(0xffffffffu, m0 < 30000u);
+            const bool try32 = !kDirect && nf == 20u && spec_skip == 0u;
             if (spec_skip) spec_skip--;
             auto run = [&](auto lut_tag, auto direct_tag) {
                 if (prior32) {
@@ -558,6 +560,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
 #ifdef SEA_ENC_DEBUG_SPEC
                 if (lane == 0 && nf == 20u) atomicAdd(fl.dbg, try32 ? (1ull << 20) : 1ull);  // failed proofs << 20 | not tried
 #endif
+                const bool narrow = __all_sync(0xffffffffu, weights_stay_narrow(w, F));
                 if (narrow && nf == 20u) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<1>{}, direct_tag);
                 else if (narrow) trial(RankTag<kRankNarrow>{}, lut_tag, LutTag<0>{}, direct_tag);
                 else trial(RankTag<kRankWide>{}, lut_tag, LutTag<0>{}, direct_tag);
@@ -611,10 +614,7 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                 chh[i] = __shfl_sync(0xffffffffu, h[i], g_lane);
             }
             prev = g_lane & (lpc - 1u);
-            if (active && lane == g_lane) {
-                if (mode == 1) vs.keys[blk * C + c] = rank;
-                else put_bits(chunk_buf, sf_sec_bit + (blk * C + c) * s, s, sf);
-            }
+            if (mode == 1 && active && lane == g_lane) vs.keys[blk * C + c] = rank;
             if (mode != 1) {  // chunk.rs:254-278: residual codes, [frame][channel], MSB first
                 // One lane per FRAME: the codes of the warp's channels are adjacent bits of the frame's row, so lane f reads every
                 // winner's code and writes them as one field of up to 32 bits (it was one lane per code: two divergent rounds of
@@ -649,6 +649,12 @@ __device__ void search_pass_fast(int mode, uint32_t uniform_size, const EncParam
                             n += sq[q];
                         }
                     put_bits(chunk_buf, res_sec_bit + blockbit + lane * rowbits + prefix0, n, field);
+                } else if (lane == 31u) {  // the block's scale factors of this warp's channels (chunk.rs:228-243): adjacent fields, one write
+                    uint32_t field = 0;
+#pragma unroll
+                    for (uint32_t q = 0; q < cpw; q++)
+                        if (q < nch) field = (field << s) | (gq[q] & (lpc - 1u));
+                    put_bits(chunk_buf, sf_sec_bit + (blk * C + cb) * s, nch * s, field);
                 }
             }
             __syncwarp();  // everybody is done with this block's samples and codes
