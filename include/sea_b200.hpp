@@ -70,6 +70,50 @@ private:
     sea_b200_ctx *ctx_ = nullptr;
 };
 
+// Every GPU of the box behind one handle (sea_b200_multi): batch calls shard the streams over the GPUs in-process --
+// one context and one host thread per GPU, nothing exchanged between them -- and report per-GPU counts.
+class MultiContext {
+public:
+    struct Shares {
+        std::vector<uint32_t> first_stream;  // index of the first stream each GPU took
+        std::vector<uint64_t> amount;        // bytes written (encode) / samples produced (decode) per GPU
+    };
+    explicit MultiContext(const std::vector<int> &devices)
+    {
+        int rc = sea_b200_multi_create(devices.data(), (uint32_t)devices.size(), &m_);
+        if (rc) throw SeaError(rc, "sea_b200_multi_create failed (libsea_b200 has no CPU fallback)");
+    }
+    ~MultiContext() { sea_b200_multi_destroy(m_); }
+    MultiContext(const MultiContext &) = delete;
+    MultiContext &operator=(const MultiContext &) = delete;
+    uint32_t device_count() const { return sea_b200_multi_device_count(m_); }
+    // n independent sea_encode calls (lib.rs:13-36) over all GPUs; arguments as sea_b200_encode_batch
+    Shares encode_batch(uint32_t n_streams, const int16_t *pcm, const uint64_t *pcm_offsets, const uint32_t *n_frames, uint32_t sample_rate,
+                        uint32_t channels, const sea_b200_settings &settings, uint8_t *out, const uint64_t *out_offsets, uint64_t *out_lens)
+    {
+        Shares sh{std::vector<uint32_t>(device_count()), std::vector<uint64_t>(device_count())};
+        check(sea_b200_multi_encode_batch(m_, n_streams, pcm, pcm_offsets, n_frames, sample_rate, channels, &settings, out, out_offsets, out_lens,
+                                          sh.first_stream.data(), sh.amount.data()));
+        return sh;
+    }
+    // n independent sea_decode calls (lib.rs:44-63) over all GPUs; arguments as sea_b200_decode_batch
+    Shares decode_batch(uint32_t n_streams, const uint8_t *sea, const uint64_t *sea_offsets, const uint64_t *sea_lens, int16_t *pcm,
+                        const uint64_t *pcm_offsets, const uint64_t *pcm_caps, uint64_t *n_samples)
+    {
+        Shares sh{std::vector<uint32_t>(device_count()), std::vector<uint64_t>(device_count())};
+        check(sea_b200_multi_decode_batch(m_, n_streams, sea, sea_offsets, sea_lens, pcm, pcm_offsets, pcm_caps, n_samples,
+                                          sh.first_stream.data(), sh.amount.data()));
+        return sh;
+    }
+
+private:
+    void check(int rc) const
+    {
+        if (rc < 0) throw SeaError(rc, sea_b200_multi_last_error(m_));
+    }
+    sea_b200_multi *m_ = nullptr;
+};
+
 // In-memory reader/writer with the std::io::Read / Write shape the reference is generic over.
 struct SliceReader {
     const uint8_t *p;

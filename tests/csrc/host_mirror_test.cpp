@@ -77,6 +77,39 @@ int main(int argc, char **argv)
             fprintf(stderr, "sea_decode_range differs from the slice of the full decode\n");
             return 1;
         }
+        // the in-process multi-GPU calls (here: two contexts on GPU 0) on a batch of three copies: same bytes, same samples
+        {
+            sea::MultiContext multi({0, 0});
+            const uint32_t nb = 3, frames = (uint32_t)(n / channels);
+            std::vector<int16_t> batch(nb * n);
+            for (uint32_t i = 0; i < nb; i++) memcpy(batch.data() + i * n, pcm, n * 2);
+            uint64_t bound = 0;
+            sea_b200_settings cst = st.c();
+            sea_b200_encode_bound(frames, channels, &cst, &bound);
+            std::vector<uint8_t> outb(nb * bound);
+            std::vector<uint64_t> po(nb), oo(nb), lens(nb), ns(nb);
+            std::vector<uint32_t> nf(nb, frames);
+            for (uint32_t i = 0; i < nb; i++) { po[i] = (uint64_t)i * n; oo[i] = (uint64_t)i * bound; }
+            sea::MultiContext::Shares sh = multi.encode_batch(nb, batch.data(), po.data(), nf.data(), rate, channels, cst, outb.data(), oo.data(), lens.data());
+            uint64_t total = 0;
+            for (uint64_t a : sh.amount) total += a;
+            for (uint32_t i = 0; i < nb; i++)
+                if (lens[i] != one.size() || memcmp(outb.data() + oo[i], one.data(), one.size()) != 0) {
+                    fprintf(stderr, "multi encode_batch stream %u differs from the one-shot encode\n", i);
+                    return 1;
+                }
+            if (total != nb * one.size() || sh.first_stream[0] != 0) {
+                fprintf(stderr, "multi encode_batch per-device counts do not add up\n");
+                return 1;
+            }
+            std::vector<int16_t> back(nb * n);
+            multi.decode_batch(nb, outb.data(), oo.data(), lens.data(), back.data(), po.data(), nullptr, ns.data());
+            for (uint32_t i = 0; i < nb; i++)
+                if (ns[i] != info.samples.size() || memcmp(back.data() + po[i], info.samples.data(), ns[i] * 2) != 0) {
+                    fprintf(stderr, "multi decode_batch stream %u differs from the one-shot decode\n", i);
+                    return 1;
+                }
+        }
         printf("ok %zu %zu %zu\n", one.size(), wr.data.size(), pcm_out.data.size());
         return 0;
     } catch (const sea::SeaError &e) {
