@@ -108,6 +108,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None  # the timed region (perf_counter): only samples that arrived inside it are reported
 
     def start(self):
         try:
@@ -120,7 +121,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -132,7 +139,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.06)]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -346,20 +354,22 @@ def main():
         kernel_ms.append(ms)
         return got
 
+    sampler = ClockSampler(info.local_rank)
+    sampler.start()  # nvidia-smi needs a few hundred ms to deliver its first line: started before the warm-up, filtered to the timed region
     for _ in range(args.warmup):
         decode_step()
     kernel_ms.clear()
-    sampler = ClockSampler(info.local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
     launches0 = ctx.launch_count
-    sampler.start()
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         got = decode_step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.end()
     clocks = sampler.stop()
     dist.barrier()
     launches = ctx.launch_count - launches0
