@@ -19,7 +19,7 @@
 //     store would.  (Earlier variants: TMA bulk stores cost ~6 ALU instructions per sample in elect/broadcast loops; an
 //     STS.U16 + LDS/STG tile copy saturated the shared-memory pipe at 85 %; 4-byte cp.async and 16-byte stores per lane hit
 //     32 sectors per instruction and choked the L1 tag stage.)
-#include "sea_kernels.h"
+#include "sea_device.cuh"
 
 #ifndef SEA_DEC_WARPS
 #define SEA_DEC_WARPS 12
@@ -27,39 +27,9 @@
 
 namespace sea {
 
+using namespace dev;
+
 namespace {
-
-__device__ __forceinline__ void report_f(int *err, int code) { atomicCAS(err, 0, code); }
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void st_global_256(void *p, const uint32_t (&v)[8])
-{
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-                 "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ int32_t lds_s32(uint32_t addr)
-{
-    int32_t v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ uint32_t find_stream_f(const DecStream *streams, uint32_t n_streams, uint64_t chain)
-{
-    uint32_t lo = 0, hi = n_streams;  // last stream whose chain_begin <= chain
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if ((uint64_t)streams[mid].chain_begin <= chain) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
 
 template <int C, int B>
 struct UCfg {
@@ -151,13 +121,13 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const bool valid = g < p.total_chunks;
     if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
 
-    const DecStream st = streams[find_stream_f(streams, p.n_streams, g * C)];
+    const DecStream st = streams[find_stream(streams, p.n_streams, g * C)];
     const uint32_t k = (uint32_t)(g - st.chain_begin / C);
     const uint64_t ck_off = st.data_off + (uint64_t)k * p.chunk_size;
     const uint8_t *ck = sea + ck_off;
     {
         const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
-        if (word != p.hdr_word) report_f(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
+        if (word != p.hdr_word) report(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
     }
     int32_t w[C][4], h[C][4], sg[C][4];
 #pragma unroll
@@ -218,7 +188,7 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
         // my buffer (r+1)&1 was consumed in round r-1 (only I read my row): refill it, then wait for this round's slice
         if (r + 1 < n_rounds) issue_round(r + 1);
         else cp_async_commit();
-        cp_async_wait1();
+        cp_async_wait<1>();
         // byte offset of the round's first residual byte inside its staged row (the row starts at a 16-byte boundary of the file)
         const uint32_t rb = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & 15u;
         const uint32_t row_sh = my_in_sh + (r & 1u) * Cfg::kBufBytes;

@@ -9,11 +9,12 @@
 //   decode_staged_kernel   uniform batches with 1 or 2 channels: a warp owns 32/C consecutive chunks, stages
 //                          their packed residuals through shared memory with coalesced 128-bit loads, decodes
 //                          one chain per lane and stages the PCM back out for coalesced interleaved stores.
-#include "sea_kernels.h"
+#include "sea_device.cuh"
 
 namespace sea {
 
-__device__ __forceinline__ void report(int *err, int code) { atomicCAS(err, 0, code); }
+using namespace dev;
+
 
 // MSB-first field of n <= 8 bits at bit offset `bit` from p (bits.rs:42-46 semantics), p in global memory.
 __device__ __forceinline__ uint32_t get_bits_gmem(const uint8_t *p, uint64_t bit, uint32_t n)
@@ -26,16 +27,6 @@ __device__ __forceinline__ uint32_t get_bits_gmem(const uint8_t *p, uint64_t bit
 }
 
 // stream lookup: last stream whose chain_begin <= id
-__device__ __forceinline__ uint32_t find_stream(const DecStream *streams, uint32_t n_streams, uint64_t chain_id)
-{
-    uint32_t lo = 0, hi = n_streams;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if ((uint64_t)streams[mid].chain_begin <= chain_id) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
 
 // ------------------------------------------------------------------------------------------------ generic
 

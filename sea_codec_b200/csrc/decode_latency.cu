@@ -14,7 +14,7 @@
 //   C  all threads interleave the rows into the PCM output with coalesced stores.
 // Any per-chunk header (CBR / VBR, 1..8 scale-factor bits, any scale_factor_frames), any channel count up to 32, partial chunks,
 // every section checked against the bytes available exactly like decode_generic_kernel (same error codes).
-#include "sea_kernels.h"
+#include "sea_device.cuh"
 
 #ifdef SEA_LAT_DEBUG
 #include <stdio.h>
@@ -25,20 +25,9 @@
 
 namespace sea {
 
+using namespace dev;
+
 namespace {
-
-__device__ __forceinline__ void report_l(int *err, int code) { atomicCAS(err, 0, code); }
-
-__device__ __forceinline__ uint32_t find_stream_l(const DecStream *streams, uint32_t n_streams, uint64_t chain)
-{
-    uint32_t lo = 0, hi = n_streams;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if ((uint64_t)streams[mid].chain_begin <= chain) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
 
 // MSB-first field of n <= 8 bits at bit offset `bit` of a byte string in shared memory (bits.rs:42-46)
 __device__ __forceinline__ uint32_t get_bits_smem(const uint8_t *p, uint32_t bit, uint32_t n)
@@ -104,7 +93,7 @@ __global__ void __launch_bounds__(kLatThreads) decode_latency_kernel(const uint8
     if (g >= total_chunks) return;
     // streams[].chain_begin counts chains (chunk, channel); every stream of this launch has the same channel count
     const uint32_t C = streams[0].channels;
-    const DecStream st = streams[find_stream_l(streams, n_streams, g * C)];
+    const DecStream st = streams[find_stream(streams, n_streams, g * C)];
     const uint32_t k = (uint32_t)(g - st.chain_begin / C);
     const uint64_t ck_off = (uint64_t)k * st.chunk_size;
     const uint8_t *ck = sea + st.data_off + ck_off;
@@ -139,16 +128,16 @@ __global__ void __launch_bounds__(kLatThreads) decode_latency_kernel(const uint8
     // ---- header and section layout (chunk.rs:81-113), validated against the bytes available like the generic kernel (every
     // thread evaluates the same shared bytes: the early exits are CTA-uniform)
     if (take < 4u + 16u * C) {
-        if (tid == 0) report_l(err, kDevDomain);
+        if (tid == 0) report(err, kDevDomain);
         return;
     }
     const uint32_t type = cbytes[0], s = cbytes[1] >> 4, b = cbytes[1] & 15u, F = cbytes[2];
     if (type != 1u && type != 2u) {
-        if (tid == 0) report_l(err, kDevInvalidFrame);
+        if (tid == 0) report(err, kDevInvalidFrame);
         return;
     }
     if (b < 1u || b > 8u || s < 1u || s > 8u || F == 0u) {
-        if (tid == 0) report_l(err, kDevDomain);
+        if (tid == 0) report(err, kDevDomain);
         return;
     }
     const bool vbr = type == 2u;
@@ -157,7 +146,7 @@ __global__ void __launch_bounds__(kLatThreads) decode_latency_kernel(const uint8
     const uint32_t vbr_sec = sf_sec + div_ceil_u32(items * s, 8u);
     const uint32_t res_sec = vbr_sec + (vbr ? div_ceil_u32(items * 2u, 8u) : 0u);
     if (res_sec > take) {
-        if (tid == 0) report_l(err, kDevDomain);
+        if (tid == 0) report(err, kDevDomain);
         return;
     }
     const uint64_t res_bits_avail = (uint64_t)(take - res_sec) * 8u;
@@ -213,7 +202,7 @@ __global__ void __launch_bounds__(kLatThreads) decode_latency_kernel(const uint8
         for (uint32_t i = tid; i < lut_entries; i += kLatThreads) lut[i] = (int16_t)__ldg(tab + lut_first + i);
     __syncthreads();
     if (sh_verdict) {
-        if (tid == 0) report_l(err, (int)sh_verdict);
+        if (tid == 0) report(err, (int)sh_verdict);
         return;
     }
     LAT_MARK(2);

@@ -7,46 +7,14 @@
 // owns whole PCM frames: they leave as full 32-byte sectors.  Everything else is borrowed from decode_unrolled_kernel /
 // decode_vbr_kernel: per-lane cp.async ring, a window of big-endian words per body pre-shifted once so that every field
 // position inside the body is a compile-time constant, I2IP pack-saturate clamp, LMS signs carried in registers.
-#include "sea_kernels.h"
+#include "sea_device.cuh"
 
 namespace sea {
 
+using namespace dev;
+
 namespace {
 
-__device__ __forceinline__ void report_m(int *err, int code) { atomicCAS(err, 0, code); }
-__device__ __forceinline__ uint32_t smem_u32m(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16_ifm(bool pred, uint32_t dst, const void *src)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}" ::"r"((int)pred), "r"(dst), "l"(src)
-        : "memory");
-}
-__device__ __forceinline__ void cp_commit_m() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait_keep() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_wait0_m() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ uint32_t lds_u32m(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int32_t lds_s32m(uint32_t addr)
-{
-    int32_t v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t find_stream_m(const DecStream *streams, uint32_t n_streams, uint64_t chain)
-{
-    uint32_t lo = 0, hi = n_streams;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if ((uint64_t)streams[mid].chain_begin <= chain) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
 
 template <int V>
 struct ParTag {
@@ -112,7 +80,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     // dequant rows of size B as uploaded: lut[sf][code], at the start of the (1024-byte aligned) shared window so that a row's
     // base address has its low B + 2 bits clear and "row | code << 2" needs no add
     const uint32_t nwarps = blockDim.x >> 5;  // chosen per launch (launch_mc): fewer warps per CTA when the grid is only a few waves
-    const uint32_t smem_sh = smem_u32m(smem), lut_sh = (smem_sh + 1023u) & ~1023u;
+    const uint32_t smem_sh = smem_u32(smem), lut_sh = (smem_sh + 1023u) & ~1023u;
     int32_t *lut = reinterpret_cast<int32_t *>(smem + (lut_sh - smem_sh));
     for (uint32_t i = threadIdx.x; i < (1u << (s + B)); i += blockDim.x) lut[i] = tab[tab_dqt_off(s, B) + i];
     __syncthreads();
@@ -124,13 +92,13 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     const bool valid = lane < (uint32_t)(Cfg::kChunksPerWarp * Cfg::U) && g < p.total_chunks;
     if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
 
-    const DecStream st = streams[find_stream_m(streams, p.n_streams, g * CT)];
+    const DecStream st = streams[find_stream(streams, p.n_streams, g * CT)];
     const uint32_t k = (uint32_t)(g - st.chain_begin / CT);
     const uint64_t ck_off = st.data_off + (uint64_t)k * p.chunk_size;
     const uint8_t *ck = sea + ck_off;
     {
         const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
-        if (word != p.hdr_word) report_m(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
+        if (word != p.hdr_word) report(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
     }
     int32_t w[CPL][4], h[CPL][4], sg[CPL][4];
 #pragma unroll
@@ -152,15 +120,15 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     // ---- per-lane ring.  Word w of the 16-byte aligned stream sits at ring word (w & 63).
     const uint64_t a0 = res_off & ~(uint64_t)15;
     const uint8_t *src0 = sea + a0;
-    const uint32_t ring_sh = smem_u32m(smem + rings_off + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
+    const uint32_t ring_sh = smem_u32(smem + rings_off + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
     uint32_t fetched = 0;                                        // granules issued so far
     uint32_t posg = (uint32_t)(res_off - a0) * 8u;               // bit position of the current body's first field, from a0
 #pragma unroll
-    for (int t = 0; t < 16; t++) cp_async16_ifm(true, ring_sh + t * 16, src0 + t * 16);
+    for (int t = 0; t < 16; t++) cp_async16_if(true, ring_sh + t * 16, src0 + t * 16);
     fetched = 16;
-    cp_commit_m();
-    cp_commit_m();
-    cp_wait0_m();
+    cp_async_commit();
+    cp_async_commit();
+    cp_async_wait<0>();
 
     const uint32_t n_bodies = p.N / Cfg::HF;
     constexpr int kBodiesPerBlock = Cfg::F / Cfg::HF;
@@ -193,11 +161,11 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
 #pragma unroll
             for (int t = 0; t < Cfg::kTopUp; t++) {
                 const bool room = fetched * 4u + 4u <= wq + (uint32_t)Cfg::kRingWords;
-                cp_async16_ifm(room, ring_sh + (fetched & 15u) * 16u, src0 + (size_t)fetched * 16u);
+                cp_async16_if(room, ring_sh + (fetched & 15u) * 16u, src0 + (size_t)fetched * 16u);
                 fetched += room ? 1u : 0u;
             }
-            cp_commit_m();
-            cp_wait_keep<Cfg::kKeep>();
+            cp_async_commit();
+            cp_async_wait<Cfg::kKeep>();
         }
         // scale factors of this body's block (one byte per block and pair); the next block's byte is fetched a body ahead
         if ((bd % kBodiesPerBlock) == 0) {
@@ -214,7 +182,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
         const uint32_t w0 = my >> 5, sh = my & 31u;
         uint32_t V[Cfg::kNW + 1], W[Cfg::kNW];
 #pragma unroll
-        for (int t = 0; t < Cfg::kNW + 1; t++) V[t] = __byte_perm(lds_u32m(ring_sh + ((w0 + t) & 63u) * 4u), 0, 0x0123);
+        for (int t = 0; t < Cfg::kNW + 1; t++) V[t] = __byte_perm(lds_u32(ring_sh + ((w0 + t) & 63u) * 4u), 0, 0x0123);
 #pragma unroll
         for (int t = 0; t < Cfg::kNW; t++) W[t] = __funnelshift_l(V[t + 1], V[t], sh);
         posg += Cfg::kBodyBits;
@@ -245,7 +213,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
                     else if (co + B <= 32) code4 = W[cw] << ((co + B + 2 - 32) & 31);
                     else code4 = __funnelshift_r(W[cw + 1], W[cw], (64 - co - B - 2) & 31);
                 }
-                d[c] = lds_s32m((code4 & kMask4) | rowbase[c]);
+                d[c] = lds_s32((code4 & kMask4) | rowbase[c]);
                 const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                      (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                 y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:38, before the clamp

@@ -13,51 +13,14 @@
 //     ([size][sf][code], 4-byte stride).
 #include <stdlib.h>
 
-#include "sea_kernels.h"
+#include "sea_device.cuh"
 
 namespace sea {
 
+using namespace dev;
+
 namespace {
 
-__device__ __forceinline__ void report_v(int *err, int code) { atomicCAS(err, 0, code); }
-__device__ __forceinline__ uint32_t smem_u32v(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16_if(bool pred, uint32_t dst, const void *src)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}" ::"r"((int)pred), "r"(dst), "l"(src)
-        : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int32_t lds_s16v(uint32_t addr)
-{
-    int32_t v;
-    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void st_global_256v(void *p, const uint32_t (&v)[8])
-{
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-                 "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t find_stream_v(const DecStream *streams, uint32_t n_streams, uint64_t chain)
-{
-    uint32_t lo = 0, hi = n_streams;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if ((uint64_t)streams[mid].chain_begin <= chain) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
 
 template <int C>
 struct VCfg {
@@ -99,19 +62,19 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
     int16_t *lut = reinterpret_cast<int16_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
     for (uint32_t i = threadIdx.x; i < (lut_words << RS); i += blockDim.x) lut[i] = (int16_t)tab[tab_dqt_off(s, lo_size) + (i >> RS)];
     __syncthreads();
-    const uint32_t lut_sh = smem_u32v(lut) + (lane & ((1u << RS) - 1u)) * 2u;
+    const uint32_t lut_sh = smem_u32(lut) + (lane & ((1u << RS) - 1u)) * 2u;
 
     uint64_t g = ((uint64_t)blockIdx.x * Cfg::kWarps + warp) * Cfg::kRows + lane;  // global chunk index
     const bool valid = g < p.total_chunks;
     if (!valid) g = p.total_chunks - 1;  // idle lanes shadow the last chunk and never store
 
-    const DecStream st = streams[find_stream_v(streams, p.n_streams, g * C)];
+    const DecStream st = streams[find_stream(streams, p.n_streams, g * C)];
     const uint32_t k = (uint32_t)(g - st.chain_begin / C);
     const uint64_t ck_off = st.data_off + (uint64_t)k * p.chunk_size;
     const uint8_t *ck = sea + ck_off;
     {
         const uint32_t word = (uint32_t)ck[0] | ((uint32_t)ck[1] << 8) | ((uint32_t)ck[2] << 16) | ((uint32_t)ck[3] << 24);
-        if (word != p.hdr_word) report_v(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
+        if (word != p.hdr_word) report(err, kDevFallback);  // not what this kernel was specialised for: host reruns generically
     }
     int32_t w[C][4], h[C][4], sg[C][4];
 #pragma unroll
@@ -134,16 +97,16 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
     // ---- per-lane ring of residual bytes.  Word w of the 16-byte aligned stream sits at ring word (w & 31).
     const uint64_t a0 = res_off & ~(uint64_t)15;                 // aligned start of what this lane stages
     const uint8_t *src0 = sea + a0;
-    const uint32_t ring_sh = smem_u32v(smem + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
+    const uint32_t ring_sh = smem_u32(smem + warp * Cfg::kWarpBytes) + lane * Cfg::kPitch + (lane >> 3) * 16u;
     uint32_t fetched = 0;                                        // granules issued so far
     uint32_t posg = (uint32_t)(res_off - a0) * 8u;               // bit position of the next field, from a0
     const uint32_t pos_begin = posg;
 #pragma unroll
     for (int t = 0; t < 8; t++) cp_async16_if(true, ring_sh + t * 16, src0 + t * 16);
     fetched = 8;
-    cp_commit();
-    cp_commit();  // keeps the "all but the newest group" wait of the first block meaningful
-    cp_wait0();
+    cp_async_commit();
+    cp_async_commit();  // keeps the "all but the newest group" wait of the first block meaningful
+    cp_async_wait<0>();
 
     // ---- scale factors (8 bytes per round) and size codes (4 bytes per round): aligned words one round ahead, realigned and
     // byte-swapped by PRMT (per-lane byte phase), rotated at the END of a round so that nothing waits for the loads
@@ -183,8 +146,8 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
                         cp_async16_if(room, ring_sh + (fetched & 7u) * 16u, src0 + (size_t)fetched * 16u);
                         fetched += room ? 1u : 0u;
                     }
-                    cp_commit();
-                    cp_wait1();
+                    cp_async_commit();
+                    cp_async_wait<1>();
                 }
                 uint32_t size[C], rowbase[C];
                 uint32_t st_bits = 0;
@@ -216,7 +179,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
 #pragma unroll
                         for (int c = 0; c < C; c++) {
                             const uint32_t code = (c == C - 1) ? (x & m_last) : (x >> size[C - 1]);
-                            d[c] = lds_s16v(rowbase[c] + (code << (1 + RS)));
+                            d[c] = lds_s16(rowbase[c] + (code << (1 + RS)));
                             const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
                                                  (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
                             y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:74, before the clamp
@@ -248,7 +211,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
                         }
                         if (C == 2) ow[fi & 7] = packed;
                         else if (fi & 1) ow[(fi >> 1) & 7] = packed;
-                        if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256v(ob + (fi / Cfg::kOutFrames) * 32, ow);
+                        if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256(ob + (fi / Cfg::kOutFrames) * 32, ow);
                     }
                 }
             }
@@ -260,7 +223,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
         sz_b = sz_n;
     }
     // a size outside 1..8 panics in the reference (common.rs:34); more residual bits than the chunk holds is a slice error
-    if (bad || (uint64_t)(posg - pos_begin) > res_bits_avail) report_v(err, kDevFallback);
+    if (bad || (uint64_t)(posg - pos_begin) > res_bits_avail) report(err, kDevFallback);
 }
 
 bool decode_vbr_supported(const DecFastParams &p)
