@@ -263,8 +263,9 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
     std::vector<DecStream> table(job.streams);
     const bool use_vbr = fast && decode_vbr_supported(fp);  // the VBR twin of the unrolled kernel: same split, same constraints
-    // more than two channels (CBR): one lane per chunk with all its channels, decode_mc.cu; its left-overs go to the generic kernel
-    bool mc = !fast && fp.channels > 2 && (fp.hdr_word >> 24) == 0x5Au && decode_mc_supported(fp);
+    // more than two channels (CBR): one lane per chunk with all its channels, decode_mc.cu; its left-overs go to the staged kernel
+    // where that takes the channel count (3 / 5 / 7: `fast`), else to the generic one
+    bool mc = fp.channels > 2 && (fp.hdr_word >> 24) == 0x5Au && decode_mc_supported(fp);
     bool unrolled = ((fast && (use_vbr || decode_unrolled_supported(fp))) || mc) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;
     // The lane-per-chunk kernels do not look at data_len: every lane walks the layout its chunk header implies.  They therefore
     // only get chunks that are completely present, in streams whose header.chunk_size holds that layout (a crafted small
@@ -309,7 +310,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
         }
         if (chains_a == 0) unrolled = false;
     }
-    if (!unrolled) mc = false;  // no staged kernel for more than two channels: everything goes to the generic one
+    if (!unrolled) mc = false;  // everything goes to the staged kernel (`fast`) or the generic one
     CU(L.table->reserve(sizeof(DecStream) * table.size()));
     CU(cudaMemcpyAsync(L.table->p, table.data(), sizeof(DecStream) * table.size(), cudaMemcpyHostToDevice, L.stream));
     CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
@@ -327,7 +328,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
             if (fb.total_chunks) {
                 CU(cudaEventRecord(L.ev_fork, L.stream));
                 CU(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
-                if (mc) CU(launch_decode_generic(d_sea, d_pcm, d_all + 2 * (size_t)n_streams, n_streams, chains_b, ctx->tabs, L.d_err, L.side));
+                if (mc && !fast) CU(launch_decode_generic(d_sea, d_pcm, d_all + 2 * (size_t)n_streams, n_streams, chains_b, ctx->tabs, L.d_err, L.side));
                 else CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all + 2 * (size_t)n_streams, fb, ctx->tabs, L.d_err, L.side));
                 ctx->launches++;
                 CU(cudaEventRecord(L.ev_join, L.side));

@@ -53,8 +53,9 @@ bool decode_vbr_supported(const DecFastParams &p);
 cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
                               int *d_err, cudaStream_t stream);
 
-// More than two channels (decode_mc.cu): CBR, 4 / 6 / 8 channels, scale_factor_bits = 4, scale_factor_frames = 20, FULL chunks only,
-// the same alignment rules, >= 512 readable bytes after every chunk it is given.
+// More than two channels (decode_mc.cuh, decode_mc.cu, decode_mc_odd.cu): CBR, 3 .. 8 channels, scale_factor_bits <= 6,
+// scale_factor_frames = 20, FULL chunks only (frames per chunk a multiple of 20 / 40 / 80 for 4 and 8 / 6 / odd channel counts), the
+// same alignment rules, >= 512 readable bytes after every chunk it is given.
 bool decode_mc_supported(const DecFastParams &p);
 cudaError_t launch_decode_mc(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
                              int *d_err, cudaStream_t stream);

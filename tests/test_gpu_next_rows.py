@@ -311,12 +311,12 @@ def test_corrupted_files_never_disagree_with_the_oracle(ctx, oracle):
     assert n_ok >= 10 and n_err >= 10, (n_ok, n_err)
 
 
-@pytest.mark.parametrize("channels", [4, 6, 8])
+@pytest.mark.parametrize("channels", [3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_multichannel_whole_frame_kernel(ctx, oracle, channels, bits):
-    """decode_mc_kernel (one lane per chunk with all channels, whole-frame 256-bit stores; two store phases for 6 channels):
-    uniform CBR batches with 4 / 6 / 8 channels, several full chunks per stream plus a ragged tail (taken by the generic kernel
-    on the side stream), quiet / loud / ordinary signals."""
+    """decode_mc_kernel (one lane per chunk with all channels, whole-frame 256-bit stores; two store phases for 6 channels, four
+    for 3 / 5 / 7): uniform CBR batches with 3 .. 8 channels, several full chunks per stream plus a ragged tail (taken by the
+    generic resp. staged kernel on the side stream), quiet / loud / ordinary signals."""
     files, refs = [], []
     for i in range(5):
         frames = 5120 * (1 + i % 3) + (i * 997) % 5120
@@ -334,7 +334,8 @@ def test_multichannel_whole_frame_kernel(ctx, oracle, channels, bits):
         assert np.array_equal(o.samples, r)
 
 
-@pytest.mark.parametrize("channels,fpc", [(6, 5100), (6, 5080), (6, 40), (8, 1000), (8, 20), (4, 60), (4, 5100)])
+@pytest.mark.parametrize("channels,fpc", [(6, 5100), (6, 5080), (6, 40), (8, 1000), (8, 20), (4, 60), (4, 5100), (3, 5040), (3, 80), (5, 160), (7, 240),
+                                          (3, 5100), (7, 40)])
 def test_multichannel_other_chunk_lengths(ctx, oracle, channels, fpc):
     """Chunk lengths the whole-frame kernel takes (8 / 4 channels: any multiple of 20; 6 channels: multiples of 40, whose rows
     stay 32-byte aligned) and the ones that must fall through to the generic kernel (6 channels, N % 40 == 20)."""

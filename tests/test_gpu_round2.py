@@ -441,11 +441,15 @@ def test_decode_route_is_chosen_by_job_size(ctx, oracle):
 # ------------------------------------------------------------------------------------------------ odd channel counts
 
 @pytest.mark.parametrize("channels", [3, 5, 7])
-def test_odd_channel_counts_take_the_staged_kernel(ctx, oracle, channels):
-    """3 (tests/test.rs:10), 5 and 7 channels: decode_staged_kernel with 32 / C chunks per warp and idle tail lanes -- uniform
-    batches, full and partial chunks, CBR at three sizes and VBR, against the oracle."""
-    for kw in (dict(residual_bits=1.0), dict(residual_bits=3.0), dict(residual_bits=8.0), dict(residual_bits=3.0, vbr=True),
-               dict(residual_bits=5.0, scale_factor_bits=5), dict(residual_bits=4.0, scale_factor_frames=10, frames_per_chunk=1000)):
+def test_odd_channel_counts(ctx, oracle, channels):
+    """3 (tests/test.rs:10), 5 and 7 channels.  Full CBR chunks with scale_factor_frames 20 and a chunk length that is a multiple
+    of 80 frames go through decode_mc_kernel (one lane per chunk, four store phases, PCM words that straddle two frames), the
+    partial last chunks and everything else (VBR, other block lengths) through decode_staged_kernel with 32 / C chunks per warp
+    and idle tail lanes -- uniform batches, CBR at three sizes and VBR, against the oracle."""
+    for kw, launches in ((dict(residual_bits=1.0), 2), (dict(residual_bits=3.0), 2), (dict(residual_bits=8.0), 2),
+                         (dict(residual_bits=3.0, vbr=True), 1), (dict(residual_bits=5.0, scale_factor_bits=5), 2),
+                         (dict(residual_bits=4.0, scale_factor_frames=10, frames_per_chunk=1000), 1),
+                         (dict(residual_bits=3.0, frames_per_chunk=5100), 1), (dict(residual_bits=3.0, frames_per_chunk=80), 2)):
         fpc = kw.get("frames_per_chunk", 5120)
         files = [oracle.sea_encode(synth.gen_stream(1000 + 10 * channels + i, fpc * 2 + 37 * i + (i % 2) * fpc, channels, 44100), 44100, channels,
                                    oracle.make_settings(**kw)) for i in range(12)]
@@ -453,7 +457,32 @@ def test_odd_channel_counts_take_the_staged_kernel(ctx, oracle, channels):
         n0 = ctx.launch_count
         for g, w in zip(ctx.decode_batch(files), want):
             assert np.array_equal(g.samples, w), (channels, kw)
-        assert ctx.launch_count - n0 == 1, "expected one staged-kernel launch"
+        assert ctx.launch_count - n0 == launches, (kw, "whole-frame kernel + staged kernel for the tails" if launches == 2 else "one staged-kernel launch")
+
+
+@pytest.mark.parametrize("channels", [3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("sfb", [1, 3, 5, 6])
+def test_multichannel_kernel_other_scale_factor_bits(ctx, oracle, channels, sfb):
+    """decode_mc_kernel with scale_factor_bits != 4 (tests/test.rs:37 sweeps 3..5): a block's channels * s scale-factor bits start
+    at any bit phase and are cut out of a 64-bit window.  Loud, quiet and ordinary signals so that every scale factor occurs."""
+    for bits in (2.0, 5.0, 8.0):
+        files, refs = [], []
+        for i in range(4):
+            frames = 5120 * (1 + i % 2) + (i * 911) % 5120
+            if i == 1:
+                t = np.arange(frames * channels)
+                pcm = np.clip(36000 * np.sin(t * 0.013 * (1 + t % channels)), -32768, 32767).astype(np.int16)
+            elif i == 2:
+                pcm = np.random.default_rng(90 + i).integers(-300, 301, frames * channels).astype(np.int16)
+            else:
+                pcm = synth.gen_stream(1500 + i, frames, channels, 48000)
+            enc = oracle.sea_encode(pcm, 48000, channels, oracle.make_settings(bits, scale_factor_bits=sfb))
+            files.append(enc)
+            refs.append(oracle.sea_decode(enc).samples)
+        n0 = ctx.launch_count
+        for o, r in zip(ctx.decode_batch(files), refs):
+            assert np.array_equal(o.samples, r), (bits, sfb)
+        assert ctx.launch_count - n0 == 2, "expected the whole-frame kernel plus one launch for the partial last chunks"
 
 
 # ------------------------------------------------------------------------------------------------ scale_factor_bits 3 and 5 on the fast pass

@@ -20,7 +20,8 @@ elif os.environ.get("PROBE_STREAM") == "torch":
     ctx.set_stream(_ts.cuda_stream)
 frames = int(sys.argv[6]) if len(sys.argv) > 6 else secs * 44100  # argv[6]: exact frame count (e.g. a multiple of 5120: no partial chunk)
 vbr = bool(int(os.environ.get("PROBE_VBR", "0")))
-st = S.EncoderSettings(residual_bits=bits, vbr=vbr)
+sfb = int(os.environ.get("PROBE_SFB", "4"))
+st = S.EncoderSettings(residual_bits=bits, vbr=vbr, scale_factor_bits=sfb)
 u = next(k for k in range(min(n, 16), 0, -1) if n % k == 0)
 pcm = synth.gen_batch_torch(u, frames, ch, 44100, dev)
 bound = ctx.encode_bound(frames, ch, st)
@@ -43,6 +44,6 @@ if os.environ.get("PROBE_VERBOSE"):
     print("all iterations (ms):", " ".join(f"{m:.3f}" for m in ms))
 sustained = float(np.mean(ms[len(ms) // 2:])) if len(ms) >= 20 else None
 alg = n * bound + 2 * n * spp
-print(f"lib={os.path.basename(os.environ.get('SEA_B200_LIB', 'default'))} n={n} ch={ch} bits={bits}{' vbr' if vbr else ''}: best {best:.3f} ms  "
+print(f"lib={os.path.basename(os.environ.get('SEA_B200_LIB', 'default'))} n={n} ch={ch} bits={bits}{' vbr' if vbr else ''}{'' if sfb == 4 else f' sfb={sfb}'}: best {best:.3f} ms  "
       f"{n*spp/best/1e3:.0f} Msamples/s  {alg/best/1e6:.0f} GB/s ({alg/best/1e6/6550.4*100:.1f}% of HBM peak) replicas_equal={rep}"
       + (f"  sustained {sustained:.3f} ms ({alg/sustained/1e6/6550.4*100:.1f}%)" if sustained else ""))
