@@ -1,5 +1,6 @@
-// decode_vbr.cu -- the throughput decode kernel for uniform VBR batches: decode_vbr_kernel<C> (1 or 2 channels,
-// scale_factor_frames = 20, scale_factor_bits = 4, full chunks; everything else stays with decode_staged_kernel).
+// decode_vbr.cu -- the throughput decode kernel for uniform VBR batches: decode_vbr_kernel<C, RS, S4> (1 or 2 channels,
+// scale_factor_frames = 20, scale_factor_bits <= 6 -- S4: the default 4 as a compile-time constant --, full chunks; everything
+// else stays with decode_staged_kernel).
 //
 // Same mapping as decode_unrolled_kernel (decode_fast.cu): one CHUNK per lane, all C channels of it in one thread, PCM leaves
 // the registers as 256-bit stores, LMS signs carried in registers, I2IP pack-saturate clamp.  What VBR changes
@@ -45,14 +46,14 @@ struct VCfg {
 // (profiles/r02_dec_vbr3_*).  Every dequantised value fits 16 bits (|d| <= 255 * 99, dqt.rs), so the table is held as int16 and
 // every entry is replicated 2^RS times (copy lane & (2^RS - 1) is the one a lane reads): RS = 5 -- a copy per lane, two lanes per
 // bank word -- leaves at most 2-way conflicts; the launcher picks the largest RS whose table fits next to the rings.
-template <int C, int RS>
+template <int C, int RS, bool S4>
 __global__ void __launch_bounds__(VCfg<C>::kWarps * 32, 1)
 decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams, DecFastParams p,
                   const int32_t *__restrict__ tab, int *err)
 {
     using Cfg = VCfg<C>;
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr uint32_t s = 4;
+    const uint32_t s = S4 ? 4u : p.s;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t hb = p.b;                                    // chunk-header residual size
     const uint32_t lo_size = hb > 1u ? hb - 1u : 1u, hi_size = hb + 2u < 8u ? hb + 2u : 8u;
@@ -89,8 +90,8 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
     }
     const uint32_t items = (p.N / Cfg::F) * C;
     const uint64_t sf_off = ck_off + 4u + 16u * C;              // chunk.rs:108-113
-    const uint64_t vbr_off = sf_off + items / 2u;               // s == 4: two items per byte (items is even: N/F even)
-    const uint64_t res_off = vbr_off + items / 4u;              // chunk.rs:126-139: 2 bits per item
+    const uint64_t vbr_off = sf_off + (items * s + 7u) / 8u;    // the section is padded to a whole byte (bits.rs:120-128)
+    const uint64_t res_off = vbr_off + (items * 2u + 7u) / 8u;  // chunk.rs:126-139: 2 bits per item
     const uint64_t res_bits_avail = ((uint64_t)p.chunk_size - (res_off - ck_off)) * 8u;
     uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
 
@@ -113,24 +114,59 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
     const uint32_t *sfw = reinterpret_cast<const uint32_t *>(sea + (sf_off & ~(uint64_t)3));
     const uint32_t *szw = reinterpret_cast<const uint32_t *>(sea + (vbr_off & ~(uint64_t)3));
     const uint32_t sf_sel = 0x0123u + ((uint32_t)sf_off & 3u) * 0x1111u, sz_sel = 0x0123u + ((uint32_t)vbr_off & 3u) * 0x1111u;
-    uint32_t sf_a = __ldg(sfw), sf_b = __ldg(sfw + 1), sf_c = __ldg(sfw + 2), sf_n0 = 0, sf_n1 = 0;
+    uint32_t sf_a = 0, sf_b = 0, sf_c = 0, sf_n0 = 0, sf_n1 = 0;
+    if (S4) {
+        sf_a = __ldg(sfw);
+        sf_b = __ldg(sfw + 1);
+        sf_c = __ldg(sfw + 2);
+    }
     uint32_t sz_a = __ldg(szw), sz_b = __ldg(szw + 1), sz_n = 0;
+    // other scale_factor_bits: a round's 16 fields are 2 * s whole bytes (<= 12) at any byte phase -> four aligned words, a round ahead
+    uint32_t sg_w[4] = {0, 0, 0, 0}, sg_n[4] = {0, 0, 0, 0};
+    auto request_sf = [&](uint32_t r) {  // stays inside the chunk: the size codes and the residual section follow
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(sea + ((sf_off + (uint64_t)r * 2u * s) & ~(uint64_t)3));
+#pragma unroll
+        for (int j = 0; j < 4; j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sg_n[j]) : "l"(q + j));
+    };
+    if (!S4) {
+        request_sf(0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sg_w[j] = sg_n[j];
+    }
 
     const uint32_t n_rounds = p.N / Cfg::kRoundFrames;
     bool bad = false;
 
     for (uint32_t r = 0; r < n_rounds; r++) {
         // big-endian: the round's 16 scale-factor nibbles (first in the top nibble of sfr0) and 16 two-bit size codes (szr)
-        const uint32_t sfr0 = __byte_perm(sf_a, sf_b, sf_sel), sfr1 = __byte_perm(sf_b, sf_c, sf_sel);
+        uint32_t sfr0, sfr1, sfr2 = 0;  // the round's scale factors, big-endian from bit 31 of sfr0 down
+        if (S4) {
+            sfr0 = __byte_perm(sf_a, sf_b, sf_sel);
+            sfr1 = __byte_perm(sf_b, sf_c, sf_sel);
+            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_n0) : "l"(sfw + 2 * r + 3));  // both stay inside the chunk
+            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_n1) : "l"(sfw + 2 * r + 4));
+        } else {
+            const uint32_t sel = 0x0123u + (((uint32_t)sf_off + r * 2u * s) & 3u) * 0x1111u;
+            sfr0 = __byte_perm(sg_w[0], sg_w[1], sel);
+            sfr1 = __byte_perm(sg_w[1], sg_w[2], sel);
+            sfr2 = __byte_perm(sg_w[2], sg_w[3], sel);
+            if (r + 1 < n_rounds) request_sf(r + 1);
+        }
         const uint32_t szr = __byte_perm(sz_a, sz_b, sz_sel);
-        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_n0) : "l"(sfw + 2 * r + 3));  // both stay inside the chunk
-        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sf_n1) : "l"(sfw + 2 * r + 4));
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sz_n) : "l"(szw + r + 2));
 
 #pragma unroll 1
         for (uint32_t bd = 0; bd < (uint32_t)Cfg::kBodiesPerRound; bd++) {
             // items of this body: 4 (block, channel) pairs -> 4 nibbles of sfr, 4 size codes of szr
-            const uint32_t sf4 = ((bd & 2u) ? sfr1 : sfr0) >> (16u * (1u - (bd & 1u)));  // low 16 bits: this body's nibbles
+            // this body's four fields from bit 31 down
+            uint32_t sf4;
+            if (S4) {
+                sf4 = ((bd & 2u) ? sfr1 : sfr0) << (16u * (bd & 1u));
+            } else {
+                const uint32_t o = bd * 4u * s, wi = o >> 5;
+                const uint32_t a = wi == 0u ? sfr0 : (wi == 1u ? sfr1 : sfr2), b = wi == 0u ? sfr1 : (wi == 1u ? sfr2 : 0u);
+                sf4 = __funnelshift_l(b, a, o & 31u);
+            }
             const uint32_t sz4 = szr >> (24u - 8u * bd);                                    // low 8 bits: this body's codes
             uint8_t *ob = out + ((size_t)(r * Cfg::kBodiesPerRound + bd)) * (Cfg::kBodyFrames * C * 2);
             uint32_t ow[8];
@@ -154,7 +190,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     const int item = q * C + c;
-                    const uint32_t sfv = (sf4 >> (12 - 4 * item)) & 15u;
+                    const uint32_t sfv = (sf4 >> (32u - (uint32_t)(item + 1) * s)) & ((1u << s) - 1u);
                     const uint32_t sz = ((sz4 >> (6 - 2 * item)) & 3u) + hb - 1u;  // chunk.rs:136-138
                     bad |= sz < 1u || sz > 8u;
                     size[c] = sz < lo_size ? lo_size : (sz > hi_size ? hi_size : sz);  // keeps the look-up inside the table
@@ -221,6 +257,8 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
         sf_c = sf_n1;
         sz_a = sz_b;
         sz_b = sz_n;
+#pragma unroll
+        for (int j = 0; j < 4; j++) sg_w[j] = sg_n[j];
     }
     // a size outside 1..8 panics in the reference (common.rs:34); more residual bits than the chunk holds is a slice error
     if (bad || (uint64_t)(posg - pos_begin) > res_bits_avail) report(err, kDevFallback);
@@ -230,23 +268,23 @@ bool decode_vbr_supported(const DecFastParams &p)
 {
     if (p.channels != 1 && p.channels != 2) return false;
     if ((p.hdr_word & 0xffu) != 2u) return false;  // VBR chunks only
-    if (p.F != 20 || p.s != 4 || p.b < 1 || p.b > 8) return false;
+    if (p.F != 20 || p.s < 1 || p.s > 6 || p.b < 1 || p.b > 8) return false;
     const uint32_t round_frames = 640u / p.channels / 2u * 1u;  // VCfg::kRoundFrames: 160 stereo, 320 mono
     if (p.N == 0 || p.N % round_frames != 0) return false;
     return true;
 }
 
-template <int C, int RS>
+template <int C, int RS, bool S4>
 static cudaError_t launch_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, const int32_t *tab,
                               int *d_err, size_t lut_bytes, cudaStream_t stream)
 {
     using Cfg = VCfg<C>;
     const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + ((lut_bytes / 2u) << RS);
-    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C, RS, S4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
     const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
-    decode_vbr_kernel<C, RS><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    decode_vbr_kernel<C, RS, S4><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
     return cudaGetLastError();
 }
 
@@ -256,7 +294,7 @@ cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStr
     if (p.total_chunks == 0) return cudaSuccess;
     const int32_t *tab = tabs.by_s[p.s];
     const uint32_t lo = p.b > 1u ? p.b - 1u : 1u, hi = p.b + 2u < 8u ? p.b + 2u : 8u;
-    const size_t lut_bytes = (size_t)(tab_dqt_off(4, hi + 1u) - tab_dqt_off(4, lo)) * 4u;
+    const size_t lut_bytes = (size_t)(tab_dqt_off(p.s, hi + 1u) - tab_dqt_off(p.s, lo)) * 4u;
     // int16 entries, 2^RS copies.  Measured (1024 stereo 60 s streams, profiles/r02_probe2.txt): VBR-3 RS 0 / 3 / 4 / 5 = 4.75 /
     // 5.01 / 5.07 / 4.78 ms, VBR-5.5 4.99 / 5.33 / 5.51 / 5.52 ms -- the bank conflicts are not what bounds the kernel (issue
     // slots and the ALU pipe are), and the larger table costs more than the conflicts it removes: one copy is the default.
@@ -269,17 +307,19 @@ cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStr
         if (rs > 5) rs = 5;
         while (rs > 0 && ((lut_bytes / 2u) << rs) > room) rs--;
     }
-#define SEA_VBR(CC)                                                                                          \
-    switch (rs) {                                                                                            \
-        case 5: return launch_vbr<CC, 5>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
-        case 4: return launch_vbr<CC, 4>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
-        case 3: return launch_vbr<CC, 3>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
-        case 2: return launch_vbr<CC, 2>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
-        case 1: return launch_vbr<CC, 1>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);         \
-        default: return launch_vbr<CC, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+    // the tuning copies exist for the default scale_factor_bits only
+#define SEA_VBR(CC)                                                                                               \
+    if (p.s != 4u) return launch_vbr<CC, 0, false>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);    \
+    switch (rs) {                                                                                                 \
+        case 5: return launch_vbr<CC, 5, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 4: return launch_vbr<CC, 4, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 3: return launch_vbr<CC, 3, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 2: return launch_vbr<CC, 2, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 1: return launch_vbr<CC, 1, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        default: return launch_vbr<CC, 0, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);       \
     }
-    if (p.channels == 1) SEA_VBR(1)
-    SEA_VBR(2)
+    if (p.channels == 1) { SEA_VBR(1) }
+    { SEA_VBR(2) }
 #undef SEA_VBR
 }
 

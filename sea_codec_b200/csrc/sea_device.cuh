@@ -43,15 +43,21 @@ __device__ __forceinline__ int32_t lds_s16(uint32_t addr)
     return v;
 }
 
-// 16-byte global -> shared copies that bypass L1 (each lane stages its own chunk row), optionally predicated
+// 16-byte global -> shared copies that bypass L1 (each lane stages its own chunk row), optionally predicated.  SEA_CP_CA (tuning
+// builds): allocate in L1 instead, so that the second granule of a 32-byte sector hits the line the first one brought in.
+#ifdef SEA_CP_CA
+#define SEA_CP_ASYNC16 "cp.async.ca.shared.global"
+#else
+#define SEA_CP_ASYNC16 "cp.async.cg.shared.global"
+#endif
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile(SEA_CP_ASYNC16 " [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async16_if(bool pred, uint32_t dst, const void *src)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}" ::"r"((int)pred), "r"(dst), "l"(src)
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p " SEA_CP_ASYNC16 " [%1], [%2], 16;\n\t}" ::"r"((int)pred), "r"(dst), "l"(src)
         : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }

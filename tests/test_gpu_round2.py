@@ -514,3 +514,40 @@ def test_encode_fast_pass_other_scale_factor_bits(ctx, oracle, sfb, channels, pi
     for kw in (dict(residual_bits=3.0, scale_factor_bits=sfb), dict(residual_bits=3.5, vbr=True, scale_factor_bits=sfb)):
         st, ost = _settings_pair(oracle, **kw)
         assert ctx.encode_batch(streams, 44100, channels, st) == [oracle.sea_encode(x, 44100, channels, ost) for x in streams], kw
+
+
+# ------------------------------------------------------------------------------------------------ lane-per-chunk decode, other scale_factor_bits
+
+@pytest.mark.parametrize("channels", [1, 2])
+@pytest.mark.parametrize("sfb", [1, 2, 3, 5, 6, 7])
+def test_lane_per_chunk_kernels_other_scale_factor_bits(ctx, oracle, channels, sfb):
+    """decode_unrolled_kernel (CBR; scale_factor_bits 3 / 5 as compile-time instances, the rest through the run-time one) and
+    decode_vbr_kernel (VBR, scale_factor_bits <= 6) read a round's scale factors as s resp. 2 s whole bytes at any byte phase.
+    tests/test.rs:37 sweeps 3..5.  Loud / quiet / ordinary signals so that every scale factor occurs; full chunks plus a tail."""
+    cases = [dict(residual_bits=float(b), scale_factor_bits=sfb) for b in (1, 3, 4, 6, 8)]
+    if sfb <= 6:
+        cases += [dict(residual_bits=b, vbr=True, scale_factor_bits=sfb) for b in (2.0, 3.5, 5.5)]
+    for kw in cases:
+        files, refs = [], []
+        for i in range(5):
+            frames = 5120 * (2 + i % 2) + (i * 733) % 5120
+            if i == 1:
+                t = np.arange(frames * channels)
+                pcm = np.clip(37000 * np.sin(t * 0.017), -32768, 32767).astype(np.int16)
+            elif i == 2:
+                pcm = np.random.default_rng(70 + i).integers(-200, 201, frames * channels).astype(np.int16)
+            else:
+                pcm = synth.gen_stream(1700 + i, frames, channels, 44100)
+            try:
+                enc = oracle.sea_encode(pcm, 44100, channels, oracle.make_settings(**kw))
+            except oracle.OracleError:
+                break
+            files.append(enc)
+            refs.append(oracle.sea_decode(enc).samples)
+        if len(files) < 5:
+            continue
+        n0 = ctx.launch_count
+        for o, r in zip(ctx.decode_batch(files), refs):
+            assert np.array_equal(o.samples, r), kw
+        if sfb <= 5:  # the staged kernel that takes the tails holds tables up to scale_factor_bits 5; beyond that the generic kernel decodes
+            assert ctx.launch_count - n0 == 2, (kw, "expected a lane-per-chunk kernel plus the staged kernel for the partial last chunks")
