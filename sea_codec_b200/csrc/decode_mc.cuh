@@ -54,10 +54,14 @@ struct MCfg {
     static_assert((HF * CT) % 2 == 0 && kPhaseWords % 2 == 0, "a body must be whole PCM words and an even number of them");
     static constexpr int kBodyBits = HF * CT * B;       // bits of the stream one body walks through
     static constexpr int kNW = (kBodyBits + 31 + 31) / 32;  // window words from the body's first field to its last (any bit phase)
-    static constexpr int kBodyBytesMax = (kBodyBits + 7) / 8 + 1;
-    static constexpr int kRingWords = 64;               // 256-byte ring per lane: two bodies (<= 80 bytes each) plus slack
-    static constexpr int kTopUp = (kBodyBytesMax + 15) / 16 + 1;  // granules issued per body at most
-    // The ring is kept full, so the bytes of a body were issued (256 - 32) / body bytes - 1 bodies before it is decoded: that many
+    // The ring is topped up once per cycle of phases (kPhases bodies: a 4-frame body of 3 channels is 12 samples -- the ~10
+    // instructions of a top-up slot per body were 1.7 per sample there), so the unit the ring is sized for is that cycle.
+    static constexpr int kCycleBytesMax = (kPhases * kBodyBits + 7) / 8 + 1;
+    static constexpr int kTopBodies = 2 * kCycleBytesMax + 32 <= 256 ? kPhases : 1;  // bodies per top-up (7 channels x 8 bits: every body)
+    static constexpr int kBodyBytesMax = (kTopBodies * kBodyBits + 7) / 8 + 1;
+    static constexpr int kRingWords = 64;               // 256-byte ring per lane: two cycles (<= 112 bytes each) plus slack
+    static constexpr int kTopUp = (kBodyBytesMax + 15) / 16 + 1;  // granules issued per cycle at most
+    // The ring is kept full, so the bytes of a cycle were issued (256 - 32) / cycle bytes - 1 cycles before it is decoded: that many
     // of the newest groups may still be in flight.  (Waiting for all but the newest one stalled every body on loads it would
     // not need for another 4-5 bodies: long_scoreboard 1.35 per issue in profiles/r01_decode_mc_v2.)
     static constexpr int kAhead = (256 - 32) / kBodyBytesMax - 1;
@@ -66,7 +70,7 @@ struct MCfg {
     static constexpr int kWarpBytes = 32 * kPitch + 64;
     // measured: 4 channels 2.14 ms at 16 warps (2.46 at 12); 8 channels 12 warps (168 registers)
     static constexpr int kWarps = CT == 4 ? 16 : (CT == 3 ? SEA_MC_WARPS3 : SEA_MC_WARPS8);
-    static_assert(2 * kBodyBytesMax + 32 <= 256, "ring too small for two bodies");
+    static_assert(2 * kBodyBytesMax + 32 <= 256, "ring too small for two cycles of bodies");
     static constexpr int kSfBytesGeneric = (CT * 6 + 7 + 7) / 8;  // bytes that hold a block's CT * s bits at any bit phase, s <= 6
     static_assert(kSfBytesGeneric <= 8, "the scale factors of a block must fit a 64-bit window");
 };
@@ -177,8 +181,8 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     int32_t pend = 0;       // odd channel counts: the clamped last channel of an even frame, waiting for its word partner
     auto body = [&](uint32_t bd, auto parity_tag) {
         constexpr int kPhase = (decltype(parity_tag)::value * Cfg::kPhaseWords) % 8;  // words of the open 32-byte row before this body
-        // ---- top the ring up, then wait for everything but that (the bytes of this body were issued a body ago)
-        {
+        // ---- top the ring up (first body of a cycle), then wait for everything but that (the bytes of this cycle were issued a cycle ago)
+        if (decltype(parity_tag)::value % Cfg::kTopBodies == 0) {
             const uint32_t wq = posg >> 5;
 #pragma unroll
             for (int t = 0; t < Cfg::kTopUp; t++) {

@@ -1,4 +1,4 @@
-// decode_vbr.cu -- the throughput decode kernel for uniform VBR batches: decode_vbr_kernel<C, RS, S4> (1 or 2 channels,
+// decode_vbr.cu -- the throughput decode kernel for uniform VBR batches: decode_vbr_kernel<C, RS, S4, KF> (1 or 2 channels,
 // scale_factor_frames = 20, scale_factor_bits <= 6 -- S4: the default 4 as a compile-time constant --, full chunks; everything
 // else stays with decode_staged_kernel).
 //
@@ -46,7 +46,14 @@ struct VCfg {
 // (profiles/r02_dec_vbr3_*).  Every dequantised value fits 16 bits (|d| <= 255 * 99, dqt.rs), so the table is held as int16 and
 // every entry is replicated 2^RS times (copy lane & (2^RS - 1) is the one a lane reads): RS = 5 -- a copy per lane, two lanes per
 // bank word -- leaves at most 2-way conflicts; the launcher picks the largest RS whose table fits next to the rings.
-template <int C, int RS, bool S4>
+//
+// KF > 0 ("narrow" chunks: every size <= 7, i.e. header size <= 5 -- VBR up to ~5.5 bits): a window is re-read every KF frames
+// (KF * C * largest size <= 31 bits: 3 stereo frames at VBR-3 instead of 2) and is NOT shifted along: the right-shift that puts the
+// code of (frame k of the group, channel c) at bit 1 -- the int16 table's stride -- is a per-block register, and one LOP3 masks the
+// code and joins it with the row base (the table sits 1 KB-aligned, a row starts at a multiple of its own size).  A field costs
+// SHF + LOP3 + LDS (the shifting window: 4 instructions per sample), a re-read is shared by 6 samples instead of 4.  KF = 0: the
+// first form, any size.
+template <int C, int RS, bool S4, int KF>
 __global__ void __launch_bounds__(VCfg<C>::kWarps * 32, 1)
 decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams, DecFastParams p,
                   const int32_t *__restrict__ tab, int *err)
@@ -60,7 +67,9 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
 
     // ---- dequant rows of sizes lo_size..hi_size, contiguous in the uploaded table (sea_common.cuh: tab_dqt_off)
     const uint32_t lut_words = tab_dqt_off(s, hi_size + 1u) - tab_dqt_off(s, lo_size);
-    int16_t *lut = reinterpret_cast<int16_t *>(smem + Cfg::kWarps * Cfg::kWarpBytes);
+    static_assert(KF == 0 || RS == 0, "the narrow form reads the single-copy table");
+    const uint32_t lut_rel = KF ? ((smem_u32(smem) + Cfg::kWarps * Cfg::kWarpBytes + 1023u) & ~1023u) - smem_u32(smem) : Cfg::kWarps * Cfg::kWarpBytes;
+    int16_t *lut = reinterpret_cast<int16_t *>(smem + lut_rel);
     for (uint32_t i = threadIdx.x; i < (lut_words << RS); i += blockDim.x) lut[i] = (int16_t)tab[tab_dqt_off(s, lo_size) + (i >> RS)];
     __syncthreads();
     const uint32_t lut_sh = smem_u32(lut) + (lane & ((1u << RS) - 1u)) * 2u;
@@ -173,13 +182,19 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
             int32_t y_even = 0;
 #pragma unroll
             for (int q = 0; q < Cfg::kBlkPerBody; q++) {
-                // ---- top the ring up (<= 3 granules: a block consumes at most 40 bytes), then wait for everything but that
+                // ---- top the ring up (<= 3 granules: a block consumes at most 40 bytes; narrow chunks: F * C * largest size bits),
+                // then wait for everything but that.  Narrow form: the granule that lands in slot 0 is also written to the pad
+                // granule behind the ring, so that the word after ring word 31 is its neighbour and a window is [a], [a + 4].
                 {
+                    constexpr int kMaxSize = KF == 0 ? 8 : (C == 2 ? (KF >= 5 ? 3 : (KF >= 3 ? 5 : 7)) : (KF >= 6 ? 5 : (KF >= 5 ? 6 : 7)));
+                    constexpr int kTop = (Cfg::F * C * kMaxSize / 8 + 15) / 16;
                     const uint32_t wq = posg >> 5;
 #pragma unroll
-                    for (int t = 0; t < 3; t++) {
+                    for (int t = 0; t < kTop; t++) {
                         const bool room = fetched * 4u + 4u <= wq + (uint32_t)Cfg::kRingWords;
-                        cp_async16_if(room, ring_sh + (fetched & 7u) * 16u, src0 + (size_t)fetched * 16u);
+                        const uint8_t *gsrc = src0 + (size_t)fetched * 16u;
+                        cp_async16_if(room, ring_sh + (fetched & 7u) * 16u, gsrc);
+                        if (KF > 0) cp_async16_if(room && (fetched & 7u) == 0u, ring_sh + 128u, gsrc);
                         fetched += room ? 1u : 0u;
                     }
                     cp_async_commit();
@@ -191,63 +206,108 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
                 for (int c = 0; c < C; c++) {
                     const int item = q * C + c;
                     const uint32_t sfv = (sf4 >> (32u - (uint32_t)(item + 1) * s)) & ((1u << s) - 1u);
-                    const uint32_t sz = ((sz4 >> (6 - 2 * item)) & 3u) + hb - 1u;  // chunk.rs:136-138
-                    bad |= sz < 1u || sz > 8u;
-                    size[c] = sz < lo_size ? lo_size : (sz > hi_size ? hi_size : sz);  // keeps the look-up inside the table
-                    rowbase[c] = lut_sh + (((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) << (1 + RS));
+                    const uint32_t code = (sz4 >> (6 - 2 * item)) & 3u;
+                    if (KF > 0) {
+                        // header size 2..5 (launch_decode_vbr): every code is a valid size, size = lo_size + code, and the row of
+                        // (size, sf) starts 2^(s + lo_size) * (2^code - 1) + (sf << size) entries into the table
+                        size[c] = code + lo_size;
+                        rowbase[c] = lut_sh - (2u << (s + lo_size)) + ((2u << (s + lo_size)) << code) + (sfv << (size[c] + 1u));
+                    } else {
+                        const uint32_t sz = code + hb - 1u;  // chunk.rs:136-138
+                        bad |= sz < 1u || sz > 8u;
+                        size[c] = sz < lo_size ? lo_size : (sz > hi_size ? hi_size : sz);  // keeps the look-up inside the table
+                        rowbase[c] = lut_sh + (((((1u << size[c]) - (1u << lo_size)) << s) + (sfv << size[c])) << (1 + RS));
+                    }
                     st_bits += size[c];
                 }
-                const uint32_t sh_frame = 32u - st_bits;      // frame field (both channels) -> low bits
-                const uint32_t m_last = (1u << size[C - 1]) - 1u;
+                // one reconstructed frame: LMS predict / clamp / update for the C dequantised residuals, PCM into the 32-byte store
+                auto lms_frame = [&](int fi, const int32_t (&d)[C]) {
+                    int32_t y[C];
 #pragma unroll
-                for (int i0 = 0; i0 < Cfg::F; i0 += Cfg::K) {
-                    // 32 valid bits of the stream at posg (MSB first): two ring words, byte-swapped, funnel-shifted
+                    for (int c = 0; c < C; c++) {
+                        const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
+                                             (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
+                        y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:74, before the clamp
+                    }
+                    uint32_t packed = 0;
+                    int32_t sgn[C];
+#pragma unroll
+                    for (int c = 0; c < C; c++) sgn[c] = (y[c] >> 31) | 1;  // the clamp keeps the sign
+                    if (C == 2) {
+                        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[C - 1]), "r"(y[0]));
+                        y[0] = (int32_t)(int16_t)(packed & 0xffffu);
+                        y[C - 1] = (int32_t)packed >> 16;
+                    } else if ((fi & 1) == 0) {
+                        y[0] = clamp_i16(y[0]);
+                        y_even = y[0];
+                    } else {
+                        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[0]), "r"(y_even));
+                        y[0] = (int32_t)packed >> 16;
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const int32_t delta = d[c] >> 4;  // lms.rs:43-51
+                        w[c][0] += delta * sg[c][0];
+                        w[c][1] += delta * sg[c][1];
+                        w[c][2] += delta * sg[c][2];
+                        w[c][3] += delta * sg[c][3];
+                        h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
+                        sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
+                    }
+                    if (C == 2) ow[fi & 7] = packed;
+                    else if (fi & 1) ow[(fi >> 1) & 7] = packed;
+                    if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256(ob + (fi / Cfg::kOutFrames) * 32, ow);
+                };
+                // 32 valid bits of the stream at posg (MSB first): two ring words, byte-swapped, funnel-shifted
+                auto window = [&]() -> uint32_t {
                     const uint32_t wi = posg >> 5;
-                    const uint32_t r0 = lds_u32(ring_sh + (wi & 31u) * 4u), r1 = lds_u32(ring_sh + ((wi + 1u) & 31u) * 4u);
-                    uint32_t win = __funnelshift_l(__byte_perm(r1, 0, 0x0123), __byte_perm(r0, 0, 0x0123), posg & 31u);
-                    posg += (uint32_t)Cfg::K * st_bits;
+                    const uint32_t a = ring_sh + (wi & 31u) * 4u;
+                    const uint32_t r0 = lds_u32(a), r1 = KF > 0 ? lds_u32(a + 4u) : lds_u32(ring_sh + ((wi + 1u) & 31u) * 4u);
+                    return __funnelshift_l(__byte_perm(r1, 0, 0x0123), __byte_perm(r0, 0, 0x0123), posg & 31u);
+                };
+                if constexpr (KF > 0) {
+                    uint32_t shv[KF][C], mk[C];
 #pragma unroll
-                    for (int kk = 0; kk < Cfg::K; kk++) {
-                        const int fi = q * Cfg::F + i0 + kk;   // frame inside the body
-                        const uint32_t x = win >> sh_frame;
-                        win <<= st_bits;
-                        int32_t y[C], d[C];
+                    for (int c = 0; c < C; c++) {
+                        mk[c] = ((1u << size[c]) - 1u) << 1;
+                        shv[0][c] = 31u - (c == C - 1 ? st_bits : size[0]);
 #pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            const uint32_t code = (c == C - 1) ? (x & m_last) : (x >> size[C - 1]);
-                            d[c] = lds_s16(rowbase[c] + (code << (1 + RS)));
-                            const uint32_t acc = (uint32_t)w[c][0] * (uint32_t)h[c][0] + (uint32_t)w[c][1] * (uint32_t)h[c][1] +
-                                                 (uint32_t)w[c][2] * (uint32_t)h[c][2] + (uint32_t)w[c][3] * (uint32_t)h[c][3];
-                            y[c] = (int32_t)((uint32_t)((int32_t)acc >> 13) + (uint32_t)d[c]);  // codec/decoder.rs:74, before the clamp
+                        for (int kk = 1; kk < KF; kk++) shv[kk][c] = shv[kk - 1][c] - st_bits;
+                    }
+                    const uint32_t adv = (uint32_t)KF * st_bits;
+#pragma unroll
+                    for (int i0 = 0; i0 < Cfg::F; i0 += KF) {
+                        constexpr int kLast = Cfg::F % KF;  // frames of the short last group (0: none)
+                        const int G = (i0 + KF <= Cfg::F) ? KF : kLast;
+                        const uint32_t win = window();
+                        posg += G == KF ? adv : (uint32_t)G * st_bits;
+#pragma unroll
+                        for (int kk = 0; kk < G; kk++) {
+                            int32_t d[C];
+#pragma unroll
+                            for (int c = 0; c < C; c++) d[c] = lds_s16(((win >> shv[kk][c]) & mk[c]) | rowbase[c]);
+                            lms_frame(q * Cfg::F + i0 + kk, d);
                         }
-                        uint32_t packed = 0;
-                        int32_t sgn[C];
+                    }
+                } else {
+                    const uint32_t sh_frame = 32u - st_bits;      // frame field (both channels) -> low bits
+                    const uint32_t m_last = (1u << size[C - 1]) - 1u;
 #pragma unroll
-                        for (int c = 0; c < C; c++) sgn[c] = (y[c] >> 31) | 1;  // the clamp keeps the sign
-                        if (C == 2) {
-                            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[C - 1]), "r"(y[0]));
-                            y[0] = (int32_t)(int16_t)(packed & 0xffffu);
-                            y[C - 1] = (int32_t)packed >> 16;
-                        } else if ((fi & 1) == 0) {
-                            y[0] = clamp_i16(y[0]);
-                            y_even = y[0];
-                        } else {
-                            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(y[0]), "r"(y_even));
-                            y[0] = (int32_t)packed >> 16;
-                        }
+                    for (int i0 = 0; i0 < Cfg::F; i0 += Cfg::K) {
+                        uint32_t win = window();
+                        posg += (uint32_t)Cfg::K * st_bits;
 #pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            const int32_t delta = d[c] >> 4;  // lms.rs:43-51
-                            w[c][0] += delta * sg[c][0];
-                            w[c][1] += delta * sg[c][1];
-                            w[c][2] += delta * sg[c][2];
-                            w[c][3] += delta * sg[c][3];
-                            h[c][0] = h[c][1]; h[c][1] = h[c][2]; h[c][2] = h[c][3]; h[c][3] = y[c];
-                            sg[c][0] = sg[c][1]; sg[c][1] = sg[c][2]; sg[c][2] = sg[c][3]; sg[c][3] = sgn[c];
+                        for (int kk = 0; kk < Cfg::K; kk++) {
+                            const uint32_t x = win >> sh_frame;
+                            win <<= st_bits;
+                            int32_t d[C];
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                const uint32_t code = (c == C - 1) ? (x & m_last) : (x >> size[C - 1]);
+                                d[c] = lds_s16(rowbase[c] + (code << (1 + RS)));
+                            }
+                            lms_frame(q * Cfg::F + i0 + kk, d);
                         }
-                        if (C == 2) ow[fi & 7] = packed;
-                        else if (fi & 1) ow[(fi >> 1) & 7] = packed;
-                        if ((fi % Cfg::kOutFrames) == Cfg::kOutFrames - 1 && valid) st_global_256(ob + (fi / Cfg::kOutFrames) * 32, ow);
                     }
                 }
             }
@@ -274,17 +334,17 @@ bool decode_vbr_supported(const DecFastParams &p)
     return true;
 }
 
-template <int C, int RS, bool S4>
+template <int C, int RS, bool S4, int KF>
 static cudaError_t launch_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, const int32_t *tab,
                               int *d_err, size_t lut_bytes, cudaStream_t stream)
 {
     using Cfg = VCfg<C>;
-    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + ((lut_bytes / 2u) << RS);
-    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C, RS, S4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)Cfg::kWarps * Cfg::kWarpBytes + ((lut_bytes / 2u) << RS) + (KF ? 1024u : 0u);
+    cudaError_t e = cudaFuncSetAttribute(decode_vbr_kernel<C, RS, S4, KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t chunks_per_cta = (uint64_t)Cfg::kWarps * Cfg::kRows;
     const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
-    decode_vbr_kernel<C, RS, S4><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    decode_vbr_kernel<C, RS, S4, KF><<<(unsigned)blocks, Cfg::kWarps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
     return cudaGetLastError();
 }
 
@@ -307,16 +367,33 @@ cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStr
         if (rs > 5) rs = 5;
         while (rs > 0 && ((lut_bytes / 2u) << rs) > room) rs--;
     }
+    // Narrow chunks (every code a valid size <= 7: header size 2..5; scale_factor_bits >= 3 keeps a row aligned to its own size): the
+    // fixed-window form, re-read every KF frames with KF * C * largest size <= 31.  SEA_B200_VBR_KF=0 pins the first form.
+    const bool narrow = p.b >= 2u && hi <= 7u && p.s >= 3u && rs == 0 && !(getenv("SEA_B200_VBR_KF") && atoi(getenv("SEA_B200_VBR_KF")) == 0);
+#define SEA_VBR_N(CC, KK)                                                                                             \
+    return p.s == 4u ? launch_vbr<CC, 0, true, KK>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream)          \
+                     : launch_vbr<CC, 0, false, KK>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream)
+    if (narrow && p.channels == 1) {
+        if (hi <= 5u) SEA_VBR_N(1, 6);
+        if (hi == 6u) SEA_VBR_N(1, 5);
+        SEA_VBR_N(1, 4);
+    }
+    if (narrow) {
+        if (hi <= 3u) SEA_VBR_N(2, 5);
+        if (hi <= 5u) SEA_VBR_N(2, 3);
+        SEA_VBR_N(2, 2);
+    }
+#undef SEA_VBR_N
     // the tuning copies exist for the default scale_factor_bits only
-#define SEA_VBR(CC)                                                                                               \
-    if (p.s != 4u) return launch_vbr<CC, 0, false>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);    \
-    switch (rs) {                                                                                                 \
-        case 5: return launch_vbr<CC, 5, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
-        case 4: return launch_vbr<CC, 4, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
-        case 3: return launch_vbr<CC, 3, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
-        case 2: return launch_vbr<CC, 2, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
-        case 1: return launch_vbr<CC, 1, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
-        default: return launch_vbr<CC, 0, true>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);       \
+#define SEA_VBR(CC)                                                                                                  \
+    if (p.s != 4u) return launch_vbr<CC, 0, false, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);    \
+    switch (rs) {                                                                                                    \
+        case 5: return launch_vbr<CC, 5, true, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 4: return launch_vbr<CC, 4, true, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 3: return launch_vbr<CC, 3, true, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 2: return launch_vbr<CC, 2, true, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        case 1: return launch_vbr<CC, 1, true, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);        \
+        default: return launch_vbr<CC, 0, true, 0>(d_sea, d_pcm, d_streams, p, tab, d_err, lut_bytes, stream);       \
     }
     if (p.channels == 1) { SEA_VBR(1) }
     { SEA_VBR(2) }
