@@ -457,7 +457,7 @@ def main():
         ms_v = dist.max_over_ranks(time_decode(sea_v, stride_v, lens_v, ns, spp))
         bytes_v = float(lens_v.sum() + 2 * ns * spp)
         vbr_dec = {"value": W * ns * spp / (ms_v * 1e-3) / 1e6, "unit": "Msamples/s", "streams_per_gpu": ns, "ms_per_step": ms_v,
-                   "roofline": hbm_row(ns, bytes_v, ms_v, "decode_vbr_kernel<2>")}
+                   "roofline": hbm_row(ns, bytes_v, ms_v, "decode_vbr_kernel<2,KF=3> (fixed-window form)")}
 
         # ---- BASELINE config 3 shape (8 channels, 48 kHz, CBR 4): 256 unique 60 s streams through decode_mc_kernel
         ch8, rate8, fr8, n8 = 8, 48000, args.seconds * 48000, 256
@@ -649,14 +649,18 @@ def main():
     del pcm_out, view
     torch.cuda.empty_cache()
 
-    # ---- generic-path shapes (the reference's own tests: 3 channels, scale_factor_bits 3 and 5 -- tests/test.rs:35-64): rows that
-    # do not reach the lane-per-chunk kernels, so that the cliff is on record.  1024 unique 20 s streams each, rank 0's GPU only.
+    # ---- the other shapes of the reference's own tests (3 channels, scale_factor_bits 3 and 5 -- tests/test.rs:35-64) and what is
+    # still left to the staged kernel (3-channel VBR), so that every cliff is on record.  1024 unique 20 s streams each, rank 0's GPU.
     other = None
     if not args.skip_encode and info.rank == 0:
         other = []
-        po = torch.empty(1024 * 20 * RATE * 3, dtype=torch.int16, device=dev)
-        for chs, kw in ((3, dict(residual_bits=3.0)), (2, dict(residual_bits=3.0, scale_factor_bits=3)),
-                        (2, dict(residual_bits=3.0, scale_factor_bits=5)), (2, dict(residual_bits=3.0, scale_factor_bits=5, vbr=True))):
+        po = torch.empty(1024 * 20 * RATE * 5, dtype=torch.int16, device=dev)
+        for chs, kw, kern in ((3, dict(residual_bits=3.0), "decode_mc_kernel<3,3>"),
+                              (5, dict(residual_bits=3.0), "decode_mc_kernel<5,3>"),
+                              (2, dict(residual_bits=3.0, scale_factor_bits=3), "decode_unrolled_kernel<2,3,pair-repl,S=3>"),
+                              (2, dict(residual_bits=3.0, scale_factor_bits=5), "decode_unrolled_kernel<2,3,plain,S=5>"),
+                              (2, dict(residual_bits=3.0, scale_factor_bits=5, vbr=True), "decode_vbr_kernel<2,KF=3>"),
+                              (3, dict(residual_bits=3.0, vbr=True), "decode_staged_kernel<3,0>")):
             fr_o, n_o = 20 * RATE, 1024
             bo = Batch(torch, dev, n_o, fr_o, chs)
             ctx.synth_pcm_device(bo.pcm.data_ptr(), bo.spp, (1 << 17) + np.arange(n_o, dtype=np.uint32), fr_o, chs, RATE)
@@ -669,7 +673,7 @@ def main():
                 g, ms = decode_device(ctx, so, stride_o, lens_o, hd, po, bo.spp, n_o)
                 ks.append(ms)
             ms_do = float(np.mean(ks[1:]))
-            other.append({"channels": chs, "settings": kw, "streams": n_o, "seconds": 20,
+            other.append({"channels": chs, "settings": kw, "streams": n_o, "seconds": 20, "decode_kernel": kern,
                           "encode_msamples_per_s": n_o * bo.spp / (ms_eo * 1e-3) / 1e6,
                           "decode_msamples_per_s": n_o * bo.spp / (ms_do * 1e-3) / 1e6,
                           "decode_hbm_frac": (float(lens_o.sum()) + 2.0 * n_o * bo.spp) / (ms_do * 1e-3) / 1e9 / hbm})

@@ -53,7 +53,15 @@ struct MCfg {
     static constexpr int kPhases = kPhaseWords == 0 ? 1 : (kPhaseWords == 4 ? 2 : 4);
     static_assert((HF * CT) % 2 == 0 && kPhaseWords % 2 == 0, "a body must be whole PCM words and an even number of them");
     static constexpr int kBodyBits = HF * CT * B;       // bits of the stream one body walks through
-    static constexpr int kNW = (kBodyBits + 31 + 31) / 32;  // window words from the body's first field to its last (any bit phase)
+    // The window of pre-shifted big-endian words is loaded once per cycle of phases where that is <= 10 words (every phase is its
+    // own instantiation of the body, so the fields of a later body are compile-time positions further into the same window;
+    // 3 channels: 17 instructions per 48 samples instead of 20 per 12), else once per body.
+#ifndef SEA_MC_WIN_CYCLE
+#define SEA_MC_WIN_CYCLE 0
+#endif
+    static constexpr int kWinBodies = (SEA_MC_WIN_CYCLE && kPhases * kBodyBits <= 320) ? kPhases : 1;
+    static constexpr int kWinBits = kWinBodies * kBodyBits;
+    static constexpr int kNW = (kWinBits + 31 + 31) / 32;   // window words from the first field to the last (any bit phase)
     // The ring is topped up once per cycle of phases (kPhases bodies: a 4-frame body of 3 channels is 12 samples -- the ~10
     // instructions of a top-up slot per body were 1.7 per sample there), so the unit the ring is sized for is that cycle.
     static constexpr int kCycleBytesMax = (kPhases * kBodyBits + 7) / 8 + 1;
@@ -177,6 +185,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
     uint32_t blk_next = 0;  // the block whose scale factors are in flight
     uint32_t bib = 0;       // body inside the block
 
+    uint32_t W[Cfg::kNW];   // the window (carried across the bodies of a cycle when kWinBodies > 1)
     uint32_t ow[8];         // the 32-byte store being assembled (carried across bodies when kPhases > 1)
     int32_t pend = 0;       // odd channel counts: the clamped last channel of an even frame, waiting for its word partner
     auto body = [&](uint32_t bd, auto parity_tag) {
@@ -200,14 +209,17 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
         }
         bib = (kBodiesPerBlock == 1 || bib == (uint32_t)kBodiesPerBlock - 1u) ? 0u : bib + 1u;
 
-        // ---- window: big-endian words from the first field of this body on, pre-shifted so that it starts at bit 0 of W[0]
-        const uint32_t w0 = posg >> 5, sh = posg & 31u;
-        uint32_t V[Cfg::kNW + 1], W[Cfg::kNW];
+        // ---- window: big-endian words from the first field of this body (cycle) on, pre-shifted so that it starts at bit 0 of W[0]
+        if (decltype(parity_tag)::value % Cfg::kWinBodies == 0) {
+            const uint32_t w0 = posg >> 5, sh = posg & 31u;
+            uint32_t V[Cfg::kNW + 1];
 #pragma unroll
-        for (int t = 0; t < Cfg::kNW + 1; t++) V[t] = __byte_perm(lds_u32(ring_sh + ((w0 + t) & 63u) * 4u), 0, 0x0123);
+            for (int t = 0; t < Cfg::kNW + 1; t++) V[t] = __byte_perm(lds_u32(ring_sh + ((w0 + t) & 63u) * 4u), 0, 0x0123);
 #pragma unroll
-        for (int t = 0; t < Cfg::kNW; t++) W[t] = __funnelshift_l(V[t + 1], V[t], sh);
-        posg += Cfg::kBodyBits;
+            for (int t = 0; t < Cfg::kNW; t++) W[t] = __funnelshift_l(V[t + 1], V[t], sh);
+            posg += Cfg::kWinBits;
+        }
+        constexpr int kBit0 = (decltype(parity_tag)::value % Cfg::kWinBodies) * Cfg::kBodyBits;  // this body's first bit in W[]
 
         uint8_t *ob = out + (size_t)bd * (Cfg::kBodyWords * 4) - kPhase * 4;  // the 32-byte row this body starts in
         auto emit = [&](int wb, uint32_t word) {  // wb: word index inside the body (folds to a constant after unrolling)
@@ -218,7 +230,7 @@ decode_mc_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, con
 #pragma unroll
         for (int fi = 0; fi < Cfg::HF; fi++) {
             constexpr int kGB = CT * B;
-            const int bit = fi * CT * B;  // compile-time position of the frame's codes in W[]
+            const int bit = kBit0 + fi * CT * B;  // compile-time position of the frame's codes in W[]
             const int wd = bit >> 5, off = bit & 31;
             uint32_t x = 0;  // the frame's CT codes in the low CT*B bits, first channel highest (frames of up to 32 bits)
             if (kGB <= 32) {

@@ -36,7 +36,10 @@ struct VCfg {
     static constexpr int kRingWords = 32;            // 128-byte ring per lane
     static constexpr int kPitch = 144;               // ring + one pad granule: consecutive lanes start 4 banks apart
     static constexpr int kWarpBytes = kRows * kPitch + 64;  // rows 8j.. skewed by j granules
-    static constexpr int kWarps = 12;
+#ifndef SEA_VBR_WARPS
+#define SEA_VBR_WARPS 12
+#endif
+    static constexpr int kWarps = SEA_VBR_WARPS;
 };
 
 }  // namespace
