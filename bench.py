@@ -379,7 +379,7 @@ def main():
     assert np.all(got == spp)
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "decode_unrolled_kernel<2,3,pair-repl> (+ decode_staged_kernel<2,0> for the partial last chunks, "
+    roofline = {"bound": "hbm", "kernel": "decode_unrolled_kernel<2,3,pair-repl,S=4> (+ decode_staged_kernel<2,0> for the partial last chunks, "
                                           "side stream)",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": ncu_traffic(n, args.seconds),
                 "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,

@@ -57,7 +57,7 @@ struct MCfg {
     // own instantiation of the body, so the fields of a later body are compile-time positions further into the same window;
     // 3 channels: 17 instructions per 48 samples instead of 20 per 12), else once per body.
 #ifndef SEA_MC_WIN_CYCLE
-#define SEA_MC_WIN_CYCLE 0
+#define SEA_MC_WIN_CYCLE 1
 #endif
     static constexpr int kWinBodies = (SEA_MC_WIN_CYCLE && kPhases * kBodyBits <= 320) ? kPhases : 1;
     static constexpr int kWinBits = kWinBodies * kBodyBits;
