@@ -21,10 +21,25 @@
 //     STS.U16 + LDS/STG tile copy saturated the shared-memory pipe at 85 %; 4-byte cp.async and 16-byte stores per lane hit
 //     32 sectors per instruction and choked the L1 tag stage.)
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "sea_device.cuh"
 
 #ifndef SEA_DEC_WARPS
 #define SEA_DEC_WARPS 12
+#endif
+// PAIR (template parameter of the kernel and its configuration): stage the rows with sector-paired requests.  Otherwise every lane
+// fetches its own row, 16 bytes per cp.async: the two halves of a 32-byte sector are asked for by two different instructions
+// and L2 sends the sector twice (l1tex__m_xbar2l1tex_read_bytes = 3x the .sea bytes, profiles/r01_decode_unrolled_v12).
+// Paired: rows start at a 32-byte boundary of the file and lanes 2j / 2j+1 fetch the two halves of ONE sector of row j (then
+// row j + 16) -- the destination of a cp.async is any shared address, the source offset of the served row comes by shuffle --
+// so that each sector crosses once.  Costs 24 KB more shared memory per 12-warp CTA (rows 32 bytes longer).  Measured at 4096
+// streams (profiles/r02_s2_probe_pairfetch.txt): CBR-3 13.70 against 13.89 ms for one launch and NO difference sustained (14.67 /
+// 14.69 ms), CBR-1 2.7 % and CBR-6 4 % slower, CBR-8 2.3 % faster, mono 1.5 % slower -- the L2 -> SM over-fetch costs no time.
+// Not compiled by default (-DSEA_DEC_PAIRFETCH=1 adds the PAIR instances for full-width CTAs of the default scale_factor_bits).
+#ifndef SEA_DEC_PAIRFETCH
+#define SEA_DEC_PAIRFETCH 0
 #endif
 
 namespace sea {
@@ -33,7 +48,7 @@ using namespace dev;
 
 namespace {
 
-template <int C, int B>
+template <int C, int B, bool PAIR = false>
 struct UCfg {
     static constexpr int F = 20;                              // scale_factor_frames this kernel is unrolled for
     static constexpr int kRows = 32;                          // chunks per warp: one per lane
@@ -46,7 +61,9 @@ struct UCfg {
     static constexpr int kRoundBytes = kHalves * kHalfBytes;
     static constexpr int kNW = (kHalfBits + 31) >> 5;         // big-endian words of one half (it starts at bit 0 of W[0])
     static constexpr int kInWords = ((3 + (kHalves - 1) * kHalfBytes) >> 2) + kNW + 1;  // words a round can touch from its first word
-    static constexpr int kInGranRaw = (12 + 4 * kInWords + 15) / 16;               // 16-byte granules incl. alignment slack
+    static constexpr int kAlignSlack = PAIR ? 28 : 12;                 // word-aligned start of a round inside its staged row
+    static constexpr int kSectors = (kAlignSlack + 4 * kInWords + 31) / 32;         // 32-byte sectors of a round (paired fetch)
+    static constexpr int kInGranRaw = PAIR ? 2 * kSectors : (kAlignSlack + 4 * kInWords + 15) / 16;  // 16-byte granules incl. alignment slack
     static constexpr int kInGran = (kInGranRaw % 2) ? kInGranRaw : kInGranRaw + 1; // odd pitch: 8 rows tile all bank groups
     static constexpr int kInPitch = kInGran * 16;
     static constexpr int kBufBytes = kRows * kInPitch + 64;  // rows 8j.. are skewed by j granules: conflict-free 32-bit window reads
@@ -81,12 +98,12 @@ __host__ __device__ inline uint32_t lut0_row(int mode, uint32_t s, uint32_t b, u
 }
 
 // S: scale_factor_bits as a compile-time constant (3, 4, 5: what tests/test.rs:37 sweeps and seaconv accepts), 0 = run-time value.
-template <int C, int B, int MODE, int S>
-__global__ void __launch_bounds__(UCfg<C, B>::kWarps * 32, 1)
+template <int C, int B, int MODE, int S, bool PAIR>
+__global__ void __launch_bounds__(UCfg<C, B, PAIR>::kWarps * 32, 1)
 decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, const DecStream *__restrict__ streams,
                        DecFastParams p, const int32_t *__restrict__ tab, int *err)
 {
-    using Cfg = UCfg<C, B>;
+    using Cfg = UCfg<C, B, PAIR>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s = S ? (uint32_t)S : p.s;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -154,10 +171,23 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     // Each lane fetches its own row's next slice as 16-byte granules, one round ahead.
     const uint32_t my_in_sh = smem_u32(in_rows) + lane * Cfg::kInPitch + (lane >> 3) * 16u;
     auto issue_round = [&](uint32_t r) {
+        if constexpr (PAIR) {
+        const uint64_t mine = (res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)31;  // my row of this round, from a sector boundary
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            const uint32_t rr = (lane >> 1) + 16u * hf;  // the row this lane serves: one half of each of its sectors
+            const uint64_t so = __shfl_sync(0xffffffffu, mine, rr);
+            const uint8_t *src = sea + so + (lane & 1u) * 16u;
+            const uint32_t dst = smem_u32(in_rows) + rr * Cfg::kInPitch + (rr >> 3) * 16u + (r & 1u) * Cfg::kBufBytes + (lane & 1u) * 16u;
+#pragma unroll
+            for (int t = 0; t < Cfg::kSectors; t++) cp_async16(dst + t * 32, src + t * 32);
+        }
+        } else {
         const uint8_t *src = sea + ((res_off + (uint64_t)r * Cfg::kRoundBytes) & ~(uint64_t)15);
         const uint32_t dst = my_in_sh + (r & 1u) * Cfg::kBufBytes;
 #pragma unroll
         for (int t = 0; t < Cfg::kInGranRaw; t++) cp_async16(dst + t * 16, src + t * 16);
+        }
         cp_async_commit();
     };
     // Scale factors.  A round carries 8 fields = s whole bytes of the section: they are read as aligned 32-bit words one round
@@ -187,11 +217,13 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
 
     for (uint32_t r = 0; r < n_rounds; r++) {
         // my buffer (r+1)&1 was consumed in round r-1 (only I read my row): refill it, then wait for this round's slice
+        if (PAIR) __syncwarp();  // other lanes write my row: nobody refills a buffer that its owner may still be reading
         if (r + 1 < n_rounds) issue_round(r + 1);
         else cp_async_commit();
         cp_async_wait<1>();
+        if (PAIR) __syncwarp();  // ... and a row is complete when the lanes that fetched it have waited
         // byte offset of the round's first residual byte inside its staged row (the row starts at a 16-byte boundary of the file)
-        const uint32_t rb = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & 15u;
+        const uint32_t rb = (uint32_t)(res_off + (uint64_t)r * Cfg::kRoundBytes) & (PAIR ? 31u : 15u);
         const uint32_t row_sh = my_in_sh + (r & 1u) * Cfg::kBufBytes;
 
         uint32_t sf_round = 0, sf_round1 = 0;  // big-endian: the fields of the first / second half from bit 31 down
@@ -329,10 +361,10 @@ constexpr int unrolled_mode(int s, int b)
 }
 
 // Dynamic shared memory of a CTA of `warps` warps (pick_cta_warps): the rows of its warps plus its own copy of the tables.
-template <int C, int B>
+template <int C, int B, bool PAIR = false>
 static size_t unrolled_smem(uint32_t s, uint32_t warps)
 {
-    using Cfg = UCfg<C, B>;
+    using Cfg = UCfg<C, B, PAIR>;
     const int mode = unrolled_mode((int)s, B);
     const uint32_t l0 = lut0_bytes(mode, s, B), l1 = lut1_bytes(mode, s, B);
     return (size_t)warps * Cfg::kWarpBytes + (l0 ? (l0 < 1024u ? 1024u : l0) + l0 : 0u) + (l1 < 1024u ? 1024u : l1) + l1;
@@ -344,24 +376,41 @@ static bool plan_unrolled(uint32_t s)
     return UCfg<C, B>::kWarps >= 8 && unrolled_smem<C, B>(s, UCfg<C, B>::kWarps) <= 227u * 1024u;
 }
 
+template <int C, int B, int S, bool PAIR>
+static cudaError_t launch_unrolled_p(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
+                                     const int32_t *tab, int *d_err, uint32_t warps, cudaStream_t stream)
+{
+    using Cfg = UCfg<C, B, PAIR>;
+    constexpr int kMode = unrolled_mode(S, B);
+    const size_t smem = unrolled_smem<C, B, PAIR>(p.s, warps);
+    const uint64_t chunks_per_cta = (uint64_t)warps * Cfg::kRows;
+    const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
+    cudaError_t e = cudaFuncSetAttribute(decode_unrolled_kernel<C, B, kMode, S, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)unrolled_smem<C, B, PAIR>(p.s, Cfg::kWarps));
+    if (e != cudaSuccess) return e;
+    // The carve-out is left to the driver (the smallest that holds the resident CTAs): the kernel wants its L1 -- pinned to the
+    // maximum shared-memory carve-out the config-4 launch takes 17.4 instead of 13.9 ms (profiles/r02_s2_probe_pairfetch.txt).
+    if (getenv("SEA_B200_DEBUG_LAUNCH")) fprintf(stderr, "decode_unrolled<%d,%d,%d,%d,%d>: %u warps/CTA, %zu B smem, %llu CTAs\n", C, B, kMode, S, (int)PAIR, warps, smem, (unsigned long long)blocks);
+    decode_unrolled_kernel<C, B, kMode, S, PAIR><<<(unsigned)blocks, warps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
+    return cudaGetLastError();
+}
+
 template <int C, int B, int S>
 static cudaError_t launch_unrolled_s(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
                                      const int32_t *tab, int *d_err, cudaStream_t stream)
 {
     using Cfg = UCfg<C, B>;
-    constexpr int kMode = unrolled_mode(S, B);
     if (!plan_unrolled<C, B>(p.s)) return cudaErrorInvalidConfiguration;
-    // narrower CTAs for grids of only a few waves -- as long as every CTA's own copy of the tables still fits beside the others
+    // narrower CTAs for grids of only a few waves -- as long as the CTAs resident on an SM (each with its own copy of the tables)
+    // stay within 196 KB, which leaves the kernel 60 KB of L1
     uint32_t warps = pick_cta_warps(p.total_chunks, Cfg::kRows, Cfg::kWarps);
-    while (warps < (uint32_t)Cfg::kWarps && unrolled_smem<C, B>(p.s, warps) * (Cfg::kWarps / warps) > 220u * 1024u) warps *= 2u;
-    const size_t smem = unrolled_smem<C, B>(p.s, warps);
-    const uint64_t chunks_per_cta = (uint64_t)warps * Cfg::kRows;
-    const uint64_t blocks = (p.total_chunks + chunks_per_cta - 1) / chunks_per_cta;
-    cudaError_t e = cudaFuncSetAttribute(decode_unrolled_kernel<C, B, kMode, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)unrolled_smem<C, B>(p.s, Cfg::kWarps));
-    if (e != cudaSuccess) return e;
-    decode_unrolled_kernel<C, B, kMode, S><<<(unsigned)blocks, warps * 32, smem, stream>>>(d_sea, d_pcm, d_streams, p, tab, d_err);
-    return cudaGetLastError();
+    while (warps < (uint32_t)Cfg::kWarps && unrolled_smem<C, B>(p.s, warps) * (Cfg::kWarps / warps) > 196u * 1024u) warps *= 2u;
+    if constexpr (S == 4 && SEA_DEC_PAIRFETCH) {
+        const bool pair = warps == (uint32_t)Cfg::kWarps && UCfg<C, B, true>::kWarps == Cfg::kWarps &&
+                          unrolled_smem<C, B, true>(p.s, warps) <= 196u * 1024u && !(getenv("SEA_B200_PAIRFETCH") && getenv("SEA_B200_PAIRFETCH")[0] == '0');
+        if (pair) return launch_unrolled_p<C, B, S, true>(d_sea, d_pcm, d_streams, p, tab, d_err, warps, stream);
+    }
+    return launch_unrolled_p<C, B, S, false>(d_sea, d_pcm, d_streams, p, tab, d_err, warps, stream);
 }
 
 template <int C, int B>

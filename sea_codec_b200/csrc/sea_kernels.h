@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "sea_common.cuh"
 
@@ -76,6 +77,7 @@ inline uint32_t pick_cta_warps(uint64_t total_chunks, uint32_t chunks_per_warp, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint32_t warps = max_warps;
+    if (getenv("SEA_B200_FULL_CTAS")) return warps;  // tests / tuning: the full-width CTA (and what only it selects) whatever the job size
     while (warps > 4u && warps % 2u == 0u) {
         const uint64_t per_cta = (uint64_t)warps * chunks_per_warp;
         const uint64_t ctas = (total_chunks + per_cta - 1) / per_cta;

@@ -551,3 +551,25 @@ def test_lane_per_chunk_kernels_other_scale_factor_bits(ctx, oracle, channels, s
             assert np.array_equal(o.samples, r), kw
         if sfb <= 5:  # the staged kernel that takes the tails holds tables up to scale_factor_bits 5; beyond that the generic kernel decodes
             assert ctx.launch_count - n0 == 2, (kw, "expected a lane-per-chunk kernel plus the staged kernel for the partial last chunks")
+
+
+@pytest.mark.parametrize("channels", [1, 2])
+def test_full_width_ctas_and_sector_paired_row_fetch(ctx, oracle, channels, monkeypatch):
+    """Large jobs run the unrolled kernel as one full-width CTA per SM (small ones as several narrower CTAs, which is what every
+    other test sees): SEA_B200_FULL_CTAS pins that launch shape.  In a build with -DSEA_DEC_PAIRFETCH=1 the rows are then staged
+    by sector-paired requests (lanes 2j / 2j+1 fetch the two halves of one 32-byte sector of row j: the lane that decodes a row is
+    not the lane that fetched it) and SEA_B200_PAIRFETCH=0 switches back; in the default build both passes run the same kernel.
+    Streams of different lengths put stream boundaries inside a warp's 32 rows."""
+    monkeypatch.setenv("SEA_B200_FULL_CTAS", "1")
+    for bits in range(1, 9):
+        files, refs = [], []
+        for i in range(7):
+            frames = 5120 * (1 + (i * 5) % 4) + (i * 613) % 5120
+            pcm = synth.gen_stream(1900 + 10 * bits + i, frames, channels, 44100)
+            enc = oracle.sea_encode(pcm, 44100, channels, oracle.make_settings(float(bits)))
+            files.append(enc)
+            refs.append(oracle.sea_decode(enc).samples)
+        for flag in ("1", "0"):
+            monkeypatch.setenv("SEA_B200_PAIRFETCH", flag)
+            for o, r in zip(ctx.decode_batch(files), refs):
+                assert np.array_equal(o.samples, r), (bits, flag)

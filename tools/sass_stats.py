@@ -1,11 +1,12 @@
-"""Opcode mix of the unrolled decode body: python tools/sass_stats.py [C] [B] [MODE] [obj] [S]  (reads sea_codec_b200/build/decode_fast.o,
+"""Opcode mix of the unrolled decode body: python tools/sass_stats.py [C] [B] [MODE] [obj] [S] [PAIR]  (reads sea_codec_b200/build/decode_fast.o,
 decode_fast_mono.o for C = 1; MODE 2 = pair-replicated table, 0 = plain; S = scale_factor_bits instance 3 / 4 / 5, 0 = run-time)."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 C, B, R = (sys.argv[1:4] + ["2", "3", "2"][len(sys.argv) - 1:])[:3]
 obj = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] else os.path.join(ROOT, "sea_codec_b200", "build", "decode_fast.o" if C == "2" else "decode_fast_mono.o")
 S = sys.argv[5] if len(sys.argv) > 5 else "4"
-fun = f"_ZN3sea22decode_unrolled_kernelILi{C}ELi{B}ELi{R}ELi{S}EEEvPKhPsPKNS_9DecStreamENS_13DecFastParamsEPKiPi"
+P = sys.argv[6] if len(sys.argv) > 6 else "0"
+fun = f"_ZN3sea22decode_unrolled_kernelILi{C}ELi{B}ELi{R}ELi{S}ELb{P}EEEvPKhPsPKNS_9DecStreamENS_13DecFastParamsEPKiPi"
 sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
 ins = []
 for l in sass.splitlines():
