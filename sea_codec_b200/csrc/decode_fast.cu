@@ -13,8 +13,10 @@ bool decode_unrolled_supported(const DecFastParams &p)
     if (p.channels != 1 && p.channels != 2) return false;
     if ((p.hdr_word & 0xffu) != 1u) return false;  // CBR only
     if (p.F != 20 || p.b < 1 || p.b > 8 || p.s < 1 || p.s > 8) return false;
-    const uint32_t rf = 160u / p.channels;  // frames per staged round (UCfg::RF)
-    if (p.N % rf != 0 || p.N == 0) return false;
+    // whole halves (UCfg::HF = 40 stereo / 80 mono frames): that is also what keeps every chunk's PCM rows 32-byte aligned
+    // given N % 20 == 0 -- e.g. 5000-frame stereo chunks (62.5 rounds) end with a round of one half
+    const uint32_t hf = 80u / p.channels;
+    if (p.N % hf != 0 || p.N == 0) return false;
     return p.channels == 1 ? plan_unrolled_mono(p.b, p.s) : plan_unrolled_b<2>(p.b, p.s);
 }
 

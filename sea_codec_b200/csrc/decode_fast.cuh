@@ -166,7 +166,8 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
     const uint64_t res_off = sf_off + div_ceil_u32(items * s, 8u);
     uint8_t *out = reinterpret_cast<uint8_t *>(pcm + st.pcm_off + (uint64_t)k * p.N * C);
 
-    const uint32_t n_rounds = p.N / Cfg::RF;
+    // whole halves (decode_unrolled_supported); a chunk with an odd number of them ends with a round of one half
+    const uint32_t n_halves = p.N / Cfg::HF, n_rounds = (n_halves + Cfg::kHalves - 1u) / Cfg::kHalves;
 
     // Each lane fetches its own row's next slice as 16-byte granules, one round ahead.
     const uint32_t my_in_sh = smem_u32(in_rows) + lane * Cfg::kInPitch + (lane >> 3) * 16u;
@@ -245,7 +246,7 @@ decode_unrolled_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pc
         // further, so that the code (~24 KB) stays inside the 32 KB L1.5 instruction cache: with the round unrolled (56 KB) the
         // top stall was "no instruction" (profiles/r01_decode_unrolled_lane_per_chunk_v7).
 #pragma unroll 1
-        for (uint32_t hh = 0; hh < (uint32_t)Cfg::kHalves; hh++) {
+        for (uint32_t hh = 0; hh < (uint32_t)Cfg::kHalves && r * Cfg::kHalves + hh < n_halves; hh++) {
             const uint32_t gh = r * Cfg::kHalves + hh;
             // scale factors of this half's blocks
             uint32_t sfv[kSfFields];

@@ -146,7 +146,8 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
         for (int j = 0; j < 4; j++) sg_w[j] = sg_n[j];
     }
 
-    const uint32_t n_rounds = p.N / Cfg::kRoundFrames;
+    // whole bodies (decode_vbr_supported); the last round may hold fewer than kBodiesPerRound of them
+    const uint32_t n_bodies = p.N / Cfg::kBodyFrames, n_rounds = (n_bodies + Cfg::kBodiesPerRound - 1u) / Cfg::kBodiesPerRound;
     bool bad = false;
 
     for (uint32_t r = 0; r < n_rounds; r++) {
@@ -168,7 +169,7 @@ decode_vbr_kernel(const uint8_t *__restrict__ sea, int16_t *__restrict__ pcm, co
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sz_n) : "l"(szw + r + 2));
 
 #pragma unroll 1
-        for (uint32_t bd = 0; bd < (uint32_t)Cfg::kBodiesPerRound; bd++) {
+        for (uint32_t bd = 0; bd < (uint32_t)Cfg::kBodiesPerRound && r * Cfg::kBodiesPerRound + bd < n_bodies; bd++) {
             // items of this body: 4 (block, channel) pairs -> 4 nibbles of sfr, 4 size codes of szr
             // this body's four fields from bit 31 down
             uint32_t sf4;
@@ -332,8 +333,8 @@ bool decode_vbr_supported(const DecFastParams &p)
     if (p.channels != 1 && p.channels != 2) return false;
     if ((p.hdr_word & 0xffu) != 2u) return false;  // VBR chunks only
     if (p.F != 20 || p.s < 1 || p.s > 6 || p.b < 1 || p.b > 8) return false;
-    const uint32_t round_frames = 640u / p.channels / 2u * 1u;  // VCfg::kRoundFrames: 160 stereo, 320 mono
-    if (p.N == 0 || p.N % round_frames != 0) return false;
+    const uint32_t body_frames = 80u / p.channels;  // VCfg::kBodyFrames: 40 stereo, 80 mono (whole bodies; 32-byte aligned PCM rows)
+    if (p.N == 0 || p.N % body_frames != 0) return false;
     return true;
 }
 

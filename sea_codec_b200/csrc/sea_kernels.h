@@ -42,14 +42,14 @@ bool decode_fast_supported(const DecFastParams &p);
 cudaError_t launch_decode_fast(const uint8_t *d_sea, uint64_t sea_len, int16_t *d_pcm, const DecStream *d_streams,
                                const DecFastParams &p, DevTables tabs, int *d_err, cudaStream_t stream);
 
-// Throughput path (decode_fast.cu): CBR, 1 or 2 channels, scale_factor_frames = 20, FULL chunks only, PCM offsets
-// multiples of 8 samples, and >= 128 readable bytes after every chunk it is given (TMA rows over-read a little).
+// Throughput path (decode_fast.cuh): CBR, 1 or 2 channels, scale_factor_frames = 20, FULL chunks only (a whole number of 80-sample
+// halves), PCM offsets multiples of 16 samples, and >= 128 readable bytes after every chunk it is given (staged rows over-read a little).
 bool decode_unrolled_supported(const DecFastParams &p);
 cudaError_t launch_decode_unrolled(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p,
                                    DevTables tabs, int *d_err, cudaStream_t stream);
 
-// VBR twin (decode_vbr.cu): VBR chunks, 1 or 2 channels, scale_factor_bits = 4, scale_factor_frames = 20, FULL chunks only, the same
-// alignment rules, >= 320 readable bytes after every chunk it is given.
+// VBR twin (decode_vbr.cu): VBR chunks, 1 or 2 channels, scale_factor_bits <= 6, scale_factor_frames = 20, FULL chunks only (a whole
+// number of 80-sample bodies), the same alignment rules, >= 320 readable bytes after every chunk it is given.
 bool decode_vbr_supported(const DecFastParams &p);
 cudaError_t launch_decode_vbr(const uint8_t *d_sea, int16_t *d_pcm, const DecStream *d_streams, const DecFastParams &p, DevTables tabs,
                               int *d_err, cudaStream_t stream);

@@ -573,3 +573,30 @@ def test_full_width_ctas_and_sector_paired_row_fetch(ctx, oracle, channels, monk
             monkeypatch.setenv("SEA_B200_PAIRFETCH", flag)
             for o, r in zip(ctx.decode_batch(files), refs):
                 assert np.array_equal(o.samples, r), (bits, flag)
+
+
+@pytest.mark.parametrize("channels,fpc,lane_per_chunk", [(2, 5000, True), (2, 1000, True), (2, 200, True), (1, 5040, True), (1, 240, True),
+                                                         (2, 5020, False), (1, 5000, False)])
+def test_chunk_lengths_with_a_trailing_half_round(ctx, oracle, channels, fpc, lane_per_chunk):
+    """The unrolled and the VBR lane-per-chunk kernels stage two halves (four bodies) per round; a chunk length that is a whole
+    number of halves but not of rounds (seaconv takes any frames_per_chunk that scale_factor_frames divides: 5000-frame stereo
+    chunks are 62.5 rounds) ends with a shorter round.  Lengths that are not whole halves (their PCM rows would not stay 32-byte
+    aligned) go to the staged kernel."""
+    for kw in (dict(residual_bits=3.0), dict(residual_bits=6.0), dict(residual_bits=8.0, scale_factor_bits=5), dict(residual_bits=3.0, vbr=True),
+               dict(residual_bits=6.5, vbr=True)):
+        files, refs = [], []
+        for i in range(5):
+            frames = fpc * (3 + i % 3) + (i * 97) % fpc
+            pcm = synth.gen_stream(2100 + i, frames, channels, 44100)
+            try:
+                enc = oracle.sea_encode(pcm, 44100, channels, oracle.make_settings(frames_per_chunk=fpc, **kw))
+            except oracle.OracleError:  # a VBR bitrate whose bucket plan leaves the reference's domain at this chunk length
+                break
+            files.append(enc)
+            refs.append(oracle.sea_decode(enc).samples)
+        if len(files) < 5:
+            continue
+        n0 = ctx.launch_count
+        for o, r in zip(ctx.decode_batch(files), refs):
+            assert np.array_equal(o.samples, r), (kw, fpc)
+        assert ctx.launch_count - n0 == (2 if lane_per_chunk else 1), (kw, fpc)
