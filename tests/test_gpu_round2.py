@@ -600,3 +600,61 @@ def test_chunk_lengths_with_a_trailing_half_round(ctx, oracle, channels, fpc, la
         for o, r in zip(ctx.decode_batch(files), refs):
             assert np.array_equal(o.samples, r), (kw, fpc)
         assert ctx.launch_count - n0 == (2 if lane_per_chunk else 1), (kw, fpc)
+
+
+@pytest.mark.parametrize("seed", [20261019, 7, 424242])
+def test_randomised_batches_through_the_lane_per_chunk_kernels(ctx, oracle, seed):
+    """Seeded sweep over what the lane-per-chunk decode kernels take (scale_factor_frames 20): 1..8 channels, scale_factor_bits
+    1..6, CBR 1..8 / VBR 1.5..7.3, chunk lengths that are whole rounds, end in a short round, or must go to the staged / generic
+    kernels, ragged batches of loud / quiet / ordinary / full-scale streams, narrow and full-width CTAs.  Oracle-encoded files,
+    decoded PCM must equal the oracle's."""
+    import os
+
+    rng = np.random.default_rng(seed)
+    checked = 0
+    for case in range(72):
+        ch = int(rng.integers(1, 9))
+        sfb = int(rng.integers(1, 7))
+        fpc = 20 * int(rng.choice([2, 4, 8, 10, 12, 16, 25, 50, 63, 64, 100, 128, 250, 256]))
+        vbr = bool(rng.integers(0, 3) == 0)
+        bits = float(rng.choice([1.5, 2.0, 2.5, 3.0, 3.7, 4.2, 5.0, 5.5, 6.5, 7.3])) if vbr else float(rng.integers(1, 9))
+        kw = dict(residual_bits=bits, vbr=vbr, scale_factor_bits=sfb, frames_per_chunk=fpc)
+        files, refs = [], []
+        for i in range(int(rng.integers(2, 6))):
+            frames = fpc * int(rng.integers(1, 5)) + int(rng.integers(0, fpc))
+            kind = (case + i) % 4
+            t = np.arange(frames * ch, dtype=np.float64)
+            if kind == 0:
+                pcm = synth.gen_stream(5000 + 10 * case + i, frames, ch, 44100)
+            elif kind == 1:
+                pcm = np.clip(40000 * np.sin(t * 0.05) + rng.normal(0, 3000, t.size), -32768, 32767).astype(np.int16)
+            elif kind == 2:
+                pcm = rng.integers(-40, 41, t.size).astype(np.int16)
+            else:
+                pcm = rng.integers(-32768, 32768, t.size).astype(np.int16)
+            try:
+                enc = oracle.sea_encode(pcm, 44100, ch, oracle.make_settings(**kw))
+            except oracle.OracleError:
+                files = None
+                break
+            try:
+                want = oracle.sea_decode(enc).samples
+            except oracle.OracleError:  # a VBR plan at the edge of the reference's domain: its own decoder panics on what it wrote
+                with pytest.raises(S.SeaError):
+                    ctx.decode_batch([enc, enc])
+                files = None
+                break
+            files.append(enc)
+            refs.append(want)
+        if not files:
+            continue
+        if case % 3 == 0:
+            os.environ["SEA_B200_FULL_CTAS"] = "1"
+        try:
+            got = ctx.decode_batch(files)
+        finally:
+            os.environ.pop("SEA_B200_FULL_CTAS", None)
+        for o, r in zip(got, refs):
+            assert np.array_equal(o.samples, r), (case, ch, kw)
+        checked += 1
+    assert checked >= 50, checked
