@@ -263,7 +263,7 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     // chunks it takes and [2n, 3n) what is left for the staged kernel (partial last chunks, chunks too close to the buffer end).
     std::vector<DecStream> table(job.streams);
     const bool use_vbr = fast && decode_vbr_supported(fp);  // the VBR twin of the unrolled kernel: same split, same constraints
-    // more than two channels (CBR): one lane per chunk with all its channels, decode_mc.cu; its left-overs go to the staged kernel
+    // more than two channels (CBR): one lane per chunk with all its channels, decode_mc.cuh; its left-overs go to the staged kernel
     // where that takes the channel count (3 / 5 / 7: `fast`), else to the generic one
     bool mc = fp.channels > 2 && (fp.hdr_word >> 24) == 0x5Au && decode_mc_supported(fp);
     bool unrolled = ((fast && (use_vbr || decode_unrolled_supported(fp))) || mc) && (reinterpret_cast<uint64_t>(d_pcm) & 31u) == 0;

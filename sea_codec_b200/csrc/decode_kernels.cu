@@ -372,7 +372,8 @@ static cudaError_t launch_staged(const uint8_t *d_sea, uint64_t sea_len, int16_t
 
 bool decode_fast_supported(const DecFastParams &p)
 {
-    // 1, 2 and the odd counts the whole-frame kernel of decode_mc.cu does not take (3 is what the reference's tests use, tests/test.rs:10)
+    // 1, 2 and the odd counts (VBR, partial chunks and odd block lengths of 3 / 5 / 7 channels; their full CBR chunks go to the whole-frame
+    // kernel of decode_mc.cuh -- 3 is what the reference's tests use, tests/test.rs:10)
     if (p.channels != 1 && p.channels != 2 && p.channels != 3 && p.channels != 5 && p.channels != 7) return false;
     if (p.s < 1 || p.s > 5) return false;  // 510 << s words of LUT must fit shared memory next to the tiles
     if (p.b < 1 || p.b > 8 || p.F == 0) return false;

@@ -2,7 +2,7 @@
 // scale_factor_frames = 20, scale_factor_bits <= 6 -- S4: the default 4 as a compile-time constant --, full chunks; everything
 // else stays with decode_staged_kernel).
 //
-// Same mapping as decode_unrolled_kernel (decode_fast.cu): one CHUNK per lane, all C channels of it in one thread, PCM leaves
+// Same mapping as decode_unrolled_kernel (decode_fast.cuh): one CHUNK per lane, all C channels of it in one thread, PCM leaves
 // the registers as 256-bit stores, LMS signs carried in registers, I2IP pack-saturate clamp.  What VBR changes
 // (chunk.rs:126-139, codec/decoder.rs:52-86): every (block, channel) has its own residual size, so field positions are run-time
 // values and every lane walks its bit stream at its own pace:
