@@ -71,6 +71,11 @@ struct sea_b200_ctx {
         cudaEvent_t up[2] = {}, kern[2] = {}, down[2] = {};
         DevBuf in[2], out[2], state;
     } pipe;
+    // pipelined host-buffer decode: the error words of its groups land here (pinned) and are read once, after the last group was
+    // queued; two timing events per group
+    int *h_errs = nullptr;
+    size_t h_errs_cap = 0;
+    std::vector<cudaEvent_t> grp_ev;
     std::string last_error;
     uint64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -187,6 +192,11 @@ struct DecLane {
     DevBuf *in, *out, *table;
     int *d_err;
     double kernel_ms;
+    // deferred mode (sea_b200_decode_batch's pipeline): the throughput routes leave their error word in *defer (pinned host memory,
+    // valid once the stream has drained) instead of waiting for it, and time themselves with k0 / k1; `deferred` tells the caller
+    int *defer = nullptr;
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    bool deferred = false;
 };
 DecLane decode_lane(sea_b200_ctx *ctx, int i)
 {
@@ -316,7 +326,8 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
     CU(cudaMemsetAsync(L.d_err, 0, sizeof(int), L.stream));
     const DecStream *d_all = L.table->as<DecStream>();
 
-    CU(cudaEventRecord(L.ev0, L.stream));
+    const bool defer = L.defer && (fast || mc);
+    CU(cudaEventRecord(defer ? L.k0 : L.ev0, L.stream));
     int dev_err = 0;
     if (fast || mc) {
         if (unrolled) {
@@ -341,6 +352,13 @@ int run_decode(sea_b200_ctx *ctx, DecLane &L, DecodeJob &job, const uint8_t *d_s
         } else {
             CU(launch_decode_fast(d_sea, sea_len, d_pcm, d_all, fp, ctx->tabs, L.d_err, L.stream));
             ctx->launches++;
+        }
+        if (defer) {  // the caller reads the word after its last group (and redoes this one if it is not kDevOk)
+            CU(cudaEventRecord(L.k1, L.stream));
+            CU(cudaMemcpyAsync(L.defer, L.d_err, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+            L.deferred = true;
+            L.kernel_ms = 0.0;
+            return SEA_B200_OK;
         }
         CU(cudaMemcpyAsync(&dev_err, L.d_err, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
         CU(cudaStreamSynchronize(L.stream));
@@ -779,6 +797,8 @@ void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
     if (ctx->aux.ev0) cudaEventDestroy(ctx->aux.ev0);
     if (ctx->aux.ev1) cudaEventDestroy(ctx->aux.ev1);
     if (ctx->aux.d_err) cudaFree(ctx->aux.d_err);
+    if (ctx->h_errs) cudaFreeHost(ctx->h_errs);
+    for (cudaEvent_t e : ctx->grp_ev) cudaEventDestroy(e);
     ctx->aux.in.release();
     ctx->aux.out.release();
     ctx->aux.table.release();
@@ -952,7 +972,8 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
     };
     std::vector<Group> groups;
     {
-        const uint64_t target = 96ull << 20;  // PCM samples per group (192 MB): long enough to amortise launches, short enough to pipeline
+        uint64_t target = 96ull << 20;  // PCM samples per group (192 MB): long enough to amortise launches, short enough to pipeline
+        if (const char *env = getenv("SEA_B200_DEC_GROUP_SAMPLES")) target = std::max<uint64_t>(1, strtoull(env, nullptr, 10));  // tests, tuning
         Group g = {0, 0, UINT64_MAX, 0, UINT64_MAX, 0};
         uint64_t acc = 0;
         for (uint32_t i = 0; i < n_streams; i++) {
@@ -963,7 +984,8 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
                 g.phi = std::max(g.phi, pcm_offsets[i] + job.n_samples[i]);
             }
             acc += job.n_samples[i];
-            if (acc >= target || i + 1 == n_streams) {
+            // the first group is a short one: nothing overlaps its upload and kernels, the copy-back engine idles until they are done
+            if (acc >= (groups.empty() ? (target + 7) / 8 : target) || i + 1 == n_streams) {
                 g.i1 = i + 1;
                 if (g.phi == 0) g.plo = 0;
                 groups.push_back(g);
@@ -999,13 +1021,42 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         DecLane L = decode_lane(ctx, (int)(gi & 1));
         return cudaMemcpyAsync(L.in->p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, L.stream);
     };
+    // Deferred error words (pipelined batches): a group's kernels report through a word that the host used to wait for before it
+    // queued the group's download -- a round trip per group in front of the copy engine this entry point is bound by.  Now the
+    // whole batch is queued without a host wait, every group's word lands in pinned memory behind its kernels, and a group whose
+    // word is not kDevOk (a chunk the specialised kernel hands back, or a malformed one) is redone on its own, synchronously,
+    // after the pipeline drained.  SEA_B200_DEC_DEFER=0 keeps the wait-per-group form (A/B, tests).
+    bool defer = piped;
+    if (const char *env = getenv("SEA_B200_DEC_DEFER")) defer = piped && env[0] != '0';
+    const bool trace = getenv("SEA_B200_TRACE") != nullptr;
+    if (defer) {
+        if (ctx->h_errs_cap < groups.size()) {
+            if (ctx->h_errs) cudaFreeHost(ctx->h_errs);
+            ctx->h_errs = nullptr;
+            ctx->h_errs_cap = 0;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_errs), sizeof(int) * (groups.size() + 64), cudaHostAllocDefault));
+            ctx->h_errs_cap = groups.size() + 64;
+        }
+        memset(ctx->h_errs, 0, sizeof(int) * groups.size());
+    }
+    if (defer || trace)
+        while (ctx->grp_ev.size() < 4 * groups.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ctx->grp_ev.push_back(e);
+        }
     double kernel_ms = 0.0;
     std::vector<Run> runs;
-    CU(upload(0));
-    for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
+    std::vector<char> was_deferred(groups.size(), 0);
+    // one group through lane `lane`: kernels (+ the download of what its streams own) queued on the lane's stream
+    auto do_group = [&](size_t gi, int lane, bool deferred_mode) -> int {
         const Group &q = groups[gi];
-        if (gi + 1 < groups.size()) CU(upload(gi + 1));  // queued behind the other lane's previous download, ahead of our kernels
-        DecLane L = decode_lane(ctx, (int)(gi & 1));
+        DecLane L = decode_lane(ctx, lane);
+        if (deferred_mode) {
+            L.defer = &ctx->h_errs[gi];
+            L.k0 = ctx->grp_ev[4 * gi];
+            L.k1 = ctx->grp_ev[4 * gi + 1];
+        }
         DecodeJob sub;
         sub.streams.assign(job.streams.begin() + q.i0, job.streams.begin() + q.i1);
         sub.n_samples.assign(job.n_samples.begin() + q.i0, job.n_samples.begin() + q.i1);
@@ -1030,21 +1081,56 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
             hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
             have = true;
         }
-        rc = run_decode(ctx, L, sub, L.in->as<uint8_t>(), q.hi - q.lo, L.out->as<int16_t>(), have, hdr_word);
+        int r = run_decode(ctx, L, sub, L.in->as<uint8_t>(), q.hi - q.lo, L.out->as<int16_t>(), have, hdr_word);
         kernel_ms += L.kernel_ms;
-        if (rc == SEA_B200_OK && q.phi > q.plo) {
+        was_deferred[gi] = L.deferred;
+        if (r == SEA_B200_OK && q.phi > q.plo) {
             // only the ranges the streams own go back: whatever lies between them in the caller's buffer is not ours to touch
             // (one copy per run of adjacent streams; a packed layout is a single run)
             runs.clear();
             for (uint32_t i = q.i0; i < q.i1; i++)
                 if (job.n_samples[i]) runs.push_back({pcm_offsets[i], pcm_offsets[i] + job.n_samples[i]});
             merge_runs(runs);
-            for (const Run &r : runs)
-                CU(cudaMemcpyAsync(pcm + r.lo, L.out->as<int16_t>() + (r.lo - q.plo), (r.hi - r.lo) * 2, cudaMemcpyDeviceToHost, L.stream));
+            if (trace) CU(cudaEventRecord(ctx->grp_ev[4 * gi + 2], L.stream));
+            for (const Run &rn : runs)
+                CU(cudaMemcpyAsync(pcm + rn.lo, L.out->as<int16_t>() + (rn.lo - q.plo), (rn.hi - rn.lo) * 2, cudaMemcpyDeviceToHost, L.stream));
+            if (trace) CU(cudaEventRecord(ctx->grp_ev[4 * gi + 3], L.stream));
         }
+        return r;
+    };
+    CU(upload(0));
+    for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
+        if (gi + 1 < groups.size()) CU(upload(gi + 1));  // queued behind the other lane's previous download, ahead of our kernels
+        rc = do_group(gi, (int)(gi & 1), defer);
     }
     CU(cudaStreamSynchronize(ctx->stream));
     if (piped) CU(cudaStreamSynchronize(ctx->aux.stream));
+    if (trace && rc == SEA_B200_OK) {
+        float t_prev = 0.f;
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            float a = 0.f, b = 0.f, k = 0.f;
+            cudaEventElapsedTime(&a, ctx->grp_ev[2], ctx->grp_ev[4 * gi + 2]);
+            cudaEventElapsedTime(&b, ctx->grp_ev[2], ctx->grp_ev[4 * gi + 3]);
+            if (was_deferred[gi]) cudaEventElapsedTime(&k, ctx->grp_ev[4 * gi], ctx->grp_ev[4 * gi + 1]);
+            fprintf(stderr, "sea_b200 trace: group %zu: download starts %.3f ms (gap %.3f), takes %.3f ms = %.1f GB/s; kernels %.3f ms\n", gi, a,
+                    a - t_prev, b - a, (double)(groups[gi].phi - groups[gi].plo) * 2.0 / ((b - a) * 1e6), k);
+            t_prev = b;
+        }
+    }
+    if (defer && rc == SEA_B200_OK) {
+        for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
+            if (!was_deferred[gi]) continue;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->grp_ev[4 * gi], ctx->grp_ev[4 * gi + 1]);
+            kernel_ms += ms;
+            if (ctx->h_errs[gi] == kDevOk) continue;
+            // redo this group alone with a wait behind its kernels: run_decode falls back to the generic kernel or reports the error
+            const Group &q = groups[gi];
+            CU(cudaMemcpyAsync(ctx->in.p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, ctx->stream));
+            rc = do_group(gi, 0, false);
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     ctx->last_kernel_ms = kernel_ms;
     if (n_samples)
         for (uint32_t i = 0; i < n_streams; i++) n_samples[i] = rc == SEA_B200_OK ? job.n_samples[i] : 0;

@@ -658,3 +658,43 @@ def test_randomised_batches_through_the_lane_per_chunk_kernels(ctx, oracle, seed
             assert np.array_equal(o.samples, r), (case, ch, kw)
         checked += 1
     assert checked >= 50, checked
+
+
+# ------------------------------------------------------------------------------------------------ pipelined host-buffer decode
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("defer", ["1", "0"])
+def test_pipelined_host_batch_decode_with_deferred_error_words(ctx, oracle, monkeypatch, defer):
+    """sea_b200_decode_batch cuts a long batch into groups and queues them all without waiting for a group's error word
+    (SEA_B200_DEC_DEFER, default on); a group whose word is not clean is redone on its own afterwards.  Small groups forced by
+    SEA_B200_DEC_GROUP_SAMPLES: (1) a clean batch, (2) one chunk in a middle group whose reserved header byte is not 0x5A -- the
+    reference ignores that byte (chunk.rs:91), the specialised kernels hand the chunk back, the redo decodes it generically --,
+    (3) a chunk type the reference rejects (chunk.rs:81-85) in a middle group: the call reports InvalidFrame."""
+    ch, frames, n = 2, 5120 * 4 + 777, 14
+    files = _uniform_files(oracle, n, ch, frames, first=900, residual_bits=3.0)
+    want = [oracle.sea_decode(f).samples for f in files]
+    monkeypatch.setenv("SEA_B200_DEC_GROUP_SAMPLES", str(2 * frames * ch))  # two streams per group: 7 groups, both lanes
+    monkeypatch.setenv("SEA_B200_DEC_DEFER", defer)
+    monkeypatch.setenv("SEA_B200_DEC_LATENCY", "0")  # the throughput route is the one that defers
+    cs = files[0][6] | (files[0][7] << 8)
+    for g, w in zip(ctx.decode_batch(files), want):
+        assert np.array_equal(g.samples, w)
+    odd = list(files)
+    b = bytearray(files[7])
+    assert b[22 + 2 * cs + 3] == 0x5A
+    b[22 + 2 * cs + 3] = 0x00
+    odd[7] = bytes(b)
+    assert np.array_equal(oracle.sea_decode(odd[7]).samples, want[7])
+    for g, w in zip(ctx.decode_batch(odd), want):
+        assert np.array_equal(g.samples, w)
+    bad = list(files)
+    b = bytearray(files[9])
+    b[22 + cs] = 7
+    bad[9] = bytes(b)
+    with pytest.raises(oracle.OracleError):
+        oracle.sea_decode(bad[9])
+    with pytest.raises(S.SeaError) as e:
+        ctx.decode_batch(bad)
+    assert e.value.kind == "InvalidFrame"
+    for g, w in zip(ctx.decode_batch(files), want):  # the context is reusable after the error
+        assert np.array_equal(g.samples, w)
