@@ -384,6 +384,13 @@ def main():
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": ncu_traffic(n, args.seconds),
                 "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_msamples_per_s": samples_per_step / (k_ms * 1e-3) / 1e6}
+    # the honest ALU view: the recurrence is 23 algorithmic integer ops per sample (predict 8, unpack 2, dequant 1, add 1,
+    # clamp 2, update 9) against the measured two-pipe INT32 issue peak; the kernel executes 16.0 warp instructions per sample
+    # (profiles/r02_s2_final_dec_unrolled_4096_ncu_summary.txt: IMAD fuses multiply and add) -- it is issue-bound, not HBM-bound
+    int_peak = max(ctx.int32_peak(m)[0] for m in (0, 1, 2))
+    sps_k = samples_per_step / (k_ms * 1e-3)
+    roofline["alu_view"] = {"algorithmic_ops_per_sample": 23, "achieved_tops": sps_k * 23 / 1e12, "int32_peak_tops": int_peak / 1e12,
+                            "frac": sps_k * 23 / int_peak, "executed_instr_per_sample": 16.0, "executed_frac": sps_k * 16.0 / int_peak}
 
     # ---- parity on the benchmarked buffers, rank 0 at every N: 8 streams spread over the batch, GPU encode == oracle encode and
     # GPU decode == oracle decode (and == the reference's c/sea.h when oracle/_ref is there), bit for bit

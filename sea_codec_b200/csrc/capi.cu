@@ -76,6 +76,7 @@ struct sea_b200_ctx {
     int *h_errs = nullptr;
     size_t h_errs_cap = 0;
     std::vector<cudaEvent_t> grp_ev;
+    cudaStream_t up = nullptr;  // uploads of a pipelined batch run ahead of the lanes on their own stream
     std::string last_error;
     uint64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -798,6 +799,7 @@ void sea_b200_ctx_destroy(sea_b200_ctx *ctx)
     if (ctx->aux.ev1) cudaEventDestroy(ctx->aux.ev1);
     if (ctx->aux.d_err) cudaFree(ctx->aux.d_err);
     if (ctx->h_errs) cudaFreeHost(ctx->h_errs);
+    if (ctx->up) { cudaStreamSynchronize(ctx->up); cudaStreamDestroy(ctx->up); }
     for (cudaEvent_t e : ctx->grp_ev) cudaEventDestroy(e);
     ctx->aux.in.release();
     ctx->aux.out.release();
@@ -1008,16 +1010,45 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         max_in = std::max(max_in, q.hi - q.lo);
         max_out = std::max(max_out, q.phi - q.plo);
     }
-    CU(ctx->in.reserve(max_in + 64));
+    // Upload-ahead (pipelined batches whose .sea bytes fit a device buffer of <= 8 GB): every group's input has its own slot and
+    // all uploads are queued at once on a third stream, a lane only waits for its group's event.  Tied to the lanes (the first
+    // form: group i+2's upload queued behind group i's download) every download started together with an upload and ran 5-6 %
+    // slower for its whole length (50-53.5 against 53-57 GB/s, profiles/r02_s3_e2e_probe_*.txt); run ahead, the uploads are over
+    // after the first five groups and only those downloads are slowed (42 GB/s), the other twenty run at the link's rate: ~2 %
+    // per call.  (Plain copies show the same thing, profiles/r02_s3_copy_probe.txt: a download that STARTS while an upload is
+    // running stays slow after the upload has ended.  All downloads on one more stream of their own: no change, not kept.)
+    // SEA_B200_DEC_UPLOAD_AHEAD=0: the first form.
+    bool ahead = piped && in_bytes <= (8ull << 30);
+    if (const char *env = getenv("SEA_B200_DEC_UPLOAD_AHEAD")) ahead = ahead && env[0] != '0';
+    std::vector<uint64_t> dev_off(groups.size(), 0);  // upload-ahead: the group's slot in ctx->in (256-byte aligned: the kernels want 16)
+    if (ahead) {
+        uint64_t o = 0;
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            dev_off[gi] = o;
+            o += (groups[gi].hi - groups[gi].lo + 64 + 255) & ~255ull;
+        }
+        CU(ctx->in.reserve(o + 64));
+        if (!ctx->up) CU(cudaStreamCreateWithFlags(&ctx->up, cudaStreamNonBlocking));
+    } else {
+        CU(ctx->in.reserve(max_in + 64));
+    }
     CU(ctx->out.reserve(max_out * 2 + 64));
     if (piped) {
-        CU(ctx->aux.in.reserve(max_in + 64));
+        if (!ahead) CU(ctx->aux.in.reserve(max_in + 64));
         CU(ctx->aux.out.reserve(max_out * 2 + 64));
-        CU(cudaEventRecord(ctx->aux.ev0, ctx->stream));  // order the auxiliary lane after whatever the caller queued before us
+        CU(cudaEventRecord(ctx->aux.ev0, ctx->stream));  // order the other streams after whatever the caller queued before us
         CU(cudaStreamWaitEvent(ctx->aux.stream, ctx->aux.ev0, 0));
+        if (ahead) CU(cudaStreamWaitEvent(ctx->up, ctx->aux.ev0, 0));
     }
+    // events of group gi: kernels begin / end, download begins / ends, upload done
+    enum { kEvK0 = 0, kEvK1, kEvD0, kEvD1, kEvUp, kEvPerGroup };
+    auto gev = [&](size_t gi, int which) { return ctx->grp_ev[1 + kEvPerGroup * gi + which]; };
     auto upload = [&](size_t gi) -> cudaError_t {
         const Group &q = groups[gi];
+        if (ahead) {
+            cudaError_t e = cudaMemcpyAsync(ctx->in.as<uint8_t>() + dev_off[gi], sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, ctx->up);
+            return e != cudaSuccess ? e : cudaEventRecord(gev(gi, kEvUp), ctx->up);
+        }
         DecLane L = decode_lane(ctx, (int)(gi & 1));
         return cudaMemcpyAsync(L.in->p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, L.stream);
     };
@@ -1039,8 +1070,8 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         }
         memset(ctx->h_errs, 0, sizeof(int) * groups.size());
     }
-    if (defer || trace)
-        while (ctx->grp_ev.size() < 4 * groups.size()) {
+    if (defer || trace || ahead)
+        while (ctx->grp_ev.size() < 1 + kEvPerGroup * groups.size()) {
             cudaEvent_t e;
             CU(cudaEventCreate(&e));
             ctx->grp_ev.push_back(e);
@@ -1054,9 +1085,11 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         DecLane L = decode_lane(ctx, lane);
         if (deferred_mode) {
             L.defer = &ctx->h_errs[gi];
-            L.k0 = ctx->grp_ev[4 * gi];
-            L.k1 = ctx->grp_ev[4 * gi + 1];
+            L.k0 = gev(gi, kEvK0);
+            L.k1 = gev(gi, kEvK1);
         }
+        const uint8_t *d_in = ahead ? ctx->in.as<uint8_t>() + dev_off[gi] : L.in->as<uint8_t>();
+        if (ahead) CU(cudaStreamWaitEvent(L.stream, gev(gi, kEvUp), 0));
         DecodeJob sub;
         sub.streams.assign(job.streams.begin() + q.i0, job.streams.begin() + q.i1);
         sub.n_samples.assign(job.n_samples.begin() + q.i0, job.n_samples.begin() + q.i1);
@@ -1081,7 +1114,7 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
             hdr_word = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
             have = true;
         }
-        int r = run_decode(ctx, L, sub, L.in->as<uint8_t>(), q.hi - q.lo, L.out->as<int16_t>(), have, hdr_word);
+        int r = run_decode(ctx, L, sub, d_in, q.hi - q.lo, L.out->as<int16_t>(), have, hdr_word);
         kernel_ms += L.kernel_ms;
         was_deferred[gi] = L.deferred;
         if (r == SEA_B200_OK && q.phi > q.plo) {
@@ -1091,29 +1124,36 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
             for (uint32_t i = q.i0; i < q.i1; i++)
                 if (job.n_samples[i]) runs.push_back({pcm_offsets[i], pcm_offsets[i] + job.n_samples[i]});
             merge_runs(runs);
-            if (trace) CU(cudaEventRecord(ctx->grp_ev[4 * gi + 2], L.stream));
+            if (trace) CU(cudaEventRecord(gev(gi, kEvD0), L.stream));
             for (const Run &rn : runs)
                 CU(cudaMemcpyAsync(pcm + rn.lo, L.out->as<int16_t>() + (rn.lo - q.plo), (rn.hi - rn.lo) * 2, cudaMemcpyDeviceToHost, L.stream));
-            if (trace) CU(cudaEventRecord(ctx->grp_ev[4 * gi + 3], L.stream));
+            if (trace) CU(cudaEventRecord(gev(gi, kEvD1), L.stream));
         }
         return r;
     };
-    CU(upload(0));
+    if (trace) CU(cudaEventRecord(ctx->grp_ev[0], ctx->stream));
+    if (ahead) {
+        for (size_t gi = 0; gi < groups.size(); gi++) CU(upload(gi));
+    } else {
+        CU(upload(0));
+    }
     for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
-        if (gi + 1 < groups.size()) CU(upload(gi + 1));  // queued behind the other lane's previous download, ahead of our kernels
+        if (!ahead && gi + 1 < groups.size()) CU(upload(gi + 1));  // queued behind the other lane's previous download, ahead of our kernels
         rc = do_group(gi, (int)(gi & 1), defer);
     }
     CU(cudaStreamSynchronize(ctx->stream));
     if (piped) CU(cudaStreamSynchronize(ctx->aux.stream));
+    if (ahead) CU(cudaStreamSynchronize(ctx->up));
     if (trace && rc == SEA_B200_OK) {
         float t_prev = 0.f;
         for (size_t gi = 0; gi < groups.size(); gi++) {
-            float a = 0.f, b = 0.f, k = 0.f;
-            cudaEventElapsedTime(&a, ctx->grp_ev[2], ctx->grp_ev[4 * gi + 2]);
-            cudaEventElapsedTime(&b, ctx->grp_ev[2], ctx->grp_ev[4 * gi + 3]);
-            if (was_deferred[gi]) cudaEventElapsedTime(&k, ctx->grp_ev[4 * gi], ctx->grp_ev[4 * gi + 1]);
-            fprintf(stderr, "sea_b200 trace: group %zu: download starts %.3f ms (gap %.3f), takes %.3f ms = %.1f GB/s; kernels %.3f ms\n", gi, a,
-                    a - t_prev, b - a, (double)(groups[gi].phi - groups[gi].plo) * 2.0 / ((b - a) * 1e6), k);
+            float a = 0.f, b = 0.f, k = 0.f, u = 0.f;
+            cudaEventElapsedTime(&a, ctx->grp_ev[0], gev(gi, kEvD0));
+            cudaEventElapsedTime(&b, ctx->grp_ev[0], gev(gi, kEvD1));
+            if (was_deferred[gi]) cudaEventElapsedTime(&k, gev(gi, kEvK0), gev(gi, kEvK1));
+            if (ahead) cudaEventElapsedTime(&u, ctx->grp_ev[0], gev(gi, kEvUp));
+            fprintf(stderr, "sea_b200 trace: group %zu: upload done %.3f ms, download starts %.3f ms (gap %.3f), takes %.3f ms = %.1f GB/s; kernels %.3f ms\n",
+                    gi, u, a, a - t_prev, b - a, (double)(groups[gi].phi - groups[gi].plo) * 2.0 / ((b - a) * 1e6), k);
             t_prev = b;
         }
     }
@@ -1121,12 +1161,12 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
         for (size_t gi = 0; gi < groups.size() && rc == SEA_B200_OK; gi++) {
             if (!was_deferred[gi]) continue;
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->grp_ev[4 * gi], ctx->grp_ev[4 * gi + 1]);
+            cudaEventElapsedTime(&ms, gev(gi, kEvK0), gev(gi, kEvK1));
             kernel_ms += ms;
             if (ctx->h_errs[gi] == kDevOk) continue;
             // redo this group alone with a wait behind its kernels: run_decode falls back to the generic kernel or reports the error
             const Group &q = groups[gi];
-            CU(cudaMemcpyAsync(ctx->in.p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, ctx->stream));
+            if (!ahead) CU(cudaMemcpyAsync(ctx->in.p, sea + lo + q.lo, q.hi - q.lo, cudaMemcpyHostToDevice, ctx->stream));  // else: still in its slot
             rc = do_group(gi, 0, false);
             CU(cudaStreamSynchronize(ctx->stream));
         }

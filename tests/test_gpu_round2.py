@@ -663,10 +663,11 @@ def test_randomised_batches_through_the_lane_per_chunk_kernels(ctx, oracle, seed
 # ------------------------------------------------------------------------------------------------ pipelined host-buffer decode
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("defer", ["1", "0"])
-def test_pipelined_host_batch_decode_with_deferred_error_words(ctx, oracle, monkeypatch, defer):
+@pytest.mark.parametrize("defer,ahead", [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")])
+def test_pipelined_host_batch_decode_with_deferred_error_words(ctx, oracle, monkeypatch, defer, ahead):
     """sea_b200_decode_batch cuts a long batch into groups and queues them all without waiting for a group's error word
-    (SEA_B200_DEC_DEFER, default on); a group whose word is not clean is redone on its own afterwards.  Small groups forced by
+    (SEA_B200_DEC_DEFER, default on); a group whose word is not clean is redone on its own afterwards.  The uploads run ahead of
+    the lanes on their own stream into one slot per group (SEA_B200_DEC_UPLOAD_AHEAD, default on).  Small groups forced by
     SEA_B200_DEC_GROUP_SAMPLES: (1) a clean batch, (2) one chunk in a middle group whose reserved header byte is not 0x5A -- the
     reference ignores that byte (chunk.rs:91), the specialised kernels hand the chunk back, the redo decodes it generically --,
     (3) a chunk type the reference rejects (chunk.rs:81-85) in a middle group: the call reports InvalidFrame."""
@@ -675,6 +676,7 @@ def test_pipelined_host_batch_decode_with_deferred_error_words(ctx, oracle, monk
     want = [oracle.sea_decode(f).samples for f in files]
     monkeypatch.setenv("SEA_B200_DEC_GROUP_SAMPLES", str(2 * frames * ch))  # two streams per group: 7 groups, both lanes
     monkeypatch.setenv("SEA_B200_DEC_DEFER", defer)
+    monkeypatch.setenv("SEA_B200_DEC_UPLOAD_AHEAD", ahead)
     monkeypatch.setenv("SEA_B200_DEC_LATENCY", "0")  # the throughput route is the one that defers
     cs = files[0][6] | (files[0][7] << 8)
     for g, w in zip(ctx.decode_batch(files), want):

@@ -71,21 +71,23 @@ def control(reps=4, duplex=True):
 
 c_ms, d_ms = control(), control(duplex=False)
 print(f"control: H2D + D2H at once {c_ms:.1f} ms ({bytes_total / c_ms / 1e6:.1f} GB/s), D2H alone {d_ms:.1f} ms ({n * spp * 2 / d_ms / 1e6:.1f} GB/s)")
-for defer in ("1", "0"):
-    for grp in (24, 48, 96, 192, 384):
+for ahead, defer in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+    for grp in (48, 96, 192):
+        os.environ["SEA_B200_DEC_UPLOAD_AHEAD"] = ahead
         os.environ["SEA_B200_DEC_DEFER"] = defer
         os.environ["SEA_B200_DEC_GROUP_SAMPLES"] = str(grp << 20)
         ms = timed()
         h_pcm.zero_()
         call()
         ok = np.array_equal(h_pcm.numpy(), ref)
-        print(f"defer={defer} group={grp} Msamples: {ms:.1f} ms per call = {n * spp / ms / 1e3:.0f} Msamples/s, {c_ms / ms:.3f} of the control, bit-exact={ok}", flush=True)
+        print(f"upload_ahead={ahead} defer={defer} group={grp} Msamples: {ms:.1f} ms per call = {n * spp / ms / 1e3:.0f} Msamples/s, {c_ms / ms:.3f} of the control, bit-exact={ok}", flush=True)
 c2 = control()
 print(f"control again: {c2:.1f} ms")
-for defer in ("1", "0"):
-    os.environ["SEA_B200_DEC_DEFER"] = defer
+for ahead in ("1", "0"):
+    os.environ["SEA_B200_DEC_UPLOAD_AHEAD"] = ahead
+    os.environ["SEA_B200_DEC_DEFER"] = "1"
     os.environ["SEA_B200_DEC_GROUP_SAMPLES"] = str(96 << 20)
     os.environ["SEA_B200_TRACE"] = "1"
-    sys.stderr.write(f"--- trace, defer={defer}\n")
+    sys.stderr.write(f"--- trace, upload_ahead={ahead}\n")
     call()
     del os.environ["SEA_B200_TRACE"]
