@@ -1016,7 +1016,7 @@ int sea_b200_decode_batch(sea_b200_ctx *ctx, uint32_t n_streams, const uint8_t *
     // slower for its whole length (50-53.5 against 53-57 GB/s, profiles/r02_s3_e2e_probe_*.txt); run ahead, the uploads are over
     // after the first five groups and only those downloads are slowed (42 GB/s), the other twenty run at the link's rate: ~2 %
     // per call.  (Plain copies show the same thing, profiles/r02_s3_copy_probe.txt: a download that STARTS while an upload is
-    // running stays slow after the upload has ended.  All downloads on one more stream of their own: no change, not kept.)
+    // running stays slow after the upload has ended.  All downloads on one more stream of their own, or the uploads as five growing copies instead of one per group: no change, not kept.)
     // SEA_B200_DEC_UPLOAD_AHEAD=0: the first form.
     bool ahead = piped && in_bytes <= (8ull << 30);
     if (const char *env = getenv("SEA_B200_DEC_UPLOAD_AHEAD")) ahead = ahead && env[0] != '0';
