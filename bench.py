@@ -606,6 +606,8 @@ def main():
                "calls_per_step": calls, "streams_per_call": ne,
                "copy_ceiling_ms": copy_s * 1e3, "copy_ceiling_gbs_per_gpu": (n * bound + n * spp * 2) / copy_s / 1e9,
                "frac_of_copy_ceiling": copy_s / e2e_s,
+               "control": "plain cudaMemcpyAsync of the same bytes, one H2D and one D2H stream per rank, all ranks at once: a reference "
+                          "pattern, not a strict bound (with several ranks on one host fabric the pipelined call can beat it)",
                "sample": f"all {n} streams per step as {calls} calls of {ne} streams over the same pinned buffers; PCIe-bound"}
         # ---- e2e encode: sea_b200_encode_batch, host PCM in (2 B/sample), .sea out; a step = ns streams as ns / ne_e calls
         if not args.skip_encode:
